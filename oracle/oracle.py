@@ -1,0 +1,132 @@
+"""ctypes front end of oracle/liboracle.so (step_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  Never by the product.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+TRIANGULATE, WARP = 0, 1
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "step_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.tpo_dp.restype = C.c_float
+        _LIB.tpo_sum_energy.restype = C.c_float
+    return _LIB
+
+
+def _p(a, t=None):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def dp(NT, flavour):
+    return float(lib().tpo_dp(C.c_int(NT), C.c_int(flavour)))
+
+
+def variant_vertices(pts, tri, ratio, W, H, flavour):
+    pts, tri = _f32(pts), _i32(tri)
+    NT = tri.shape[0]
+    out = np.zeros((13 * NT, 3, 2), np.int32)
+    lib().tpo_variant_vertices(_p(pts), _p(tri), NT, C.c_float(ratio), W, H, flavour, _p(out))
+    return out
+
+
+def mode0(rgba, pts, tri, ratio, flavour, ca=None):
+    rgba, pts, tri = _u8(rgba), _f32(pts), _i32(tri)
+    H, W = rgba.shape[:2]
+    NT = tri.shape[0]
+    cn = np.zeros(13 * NT, np.int32)
+    if ca is None:
+        ca = np.zeros((13 * NT, 4), np.int32)
+    else:
+        ca = _i32(ca).copy()
+    lib().tpo_mode0(_p(rgba), W, H, _p(pts), _p(tri), NT, C.c_float(ratio), flavour, _p(cn), _p(ca))
+    return cn, ca
+
+
+def mode1(rgba, pts, tri, ratio, flavour, cn, ca, NP=None):
+    rgba, pts, tri = _u8(rgba), _f32(pts), _i32(tri)
+    H, W = rgba.shape[:2]
+    NT = tri.shape[0]
+    NP = pts.shape[0] if NP is None else NP
+    ten = np.zeros(13 * NT, np.int32)
+    gr = np.zeros((NP, 2), np.int32)
+    lib().tpo_mode1(_p(rgba), W, H, _p(pts), _p(tri), NT, C.c_float(ratio), flavour,
+                    _p(_i32(cn)), _p(_i32(ca)), _p(ten), _p(gr))
+    return ten, gr
+
+
+def gradient(tri, ten, gr):
+    tri = _i32(tri)
+    gr = _i32(gr).copy()
+    lib().tpo_gradient(_p(tri), tri.shape[0], _p(_i32(ten)), _p(gr))
+    return gr
+
+
+def shift(pts, gr, ratio, flavour):
+    pts = _f32(pts).copy()
+    lib().tpo_shift(_p(pts), pts.shape[0], _p(_i32(gr)), C.c_float(ratio), flavour)
+    return pts
+
+
+def raster_ids(pts, tri, ratio, W, H):
+    pts, tri = _f32(pts), _i32(tri)
+    ids = np.zeros((H, W), np.int32)
+    lib().tpo_raster_ids(_p(pts), _p(tri), tri.shape[0], C.c_float(ratio), W, H, _p(ids))
+    return ids
+
+
+def sum_energy(ten, NT):
+    return float(lib().tpo_sum_energy(_p(_i32(ten)), NT))
+
+
+def step(rgba, pts, tri, ratio, flavour, colors=None):
+    """One full evaluation + update at positions `pts`.
+
+    Returns dict(cn, ca, ten, gr, pts) where cn/ca/ten are the 13*NT rows at
+    the ENTRY positions and pts are the positions after the shift -- exactly
+    what the reference reads back at software/triangulate/main.cpp:201-204 /
+    software/warp/main.cpp:226-229 for that frame.
+    """
+    tri = _i32(tri)
+    NT = tri.shape[0]
+    if flavour == WARP:
+        ca = np.zeros((13 * NT, 4), np.int32)
+        col = _i32(colors).reshape(NT, 4)
+        for k in range(13):  # source/triangulation.hpp:633-641
+            ca[k * NT:(k + 1) * NT] = col
+        cn, _ = mode0(rgba, pts, tri, ratio, WARP, ca)
+    else:
+        cn, ca = mode0(rgba, pts, tri, ratio, TRIANGULATE)
+    ten, gr = mode1(rgba, pts, tri, ratio, flavour, cn, ca)
+    gr = gradient(tri, ten, gr)
+    new_pts = shift(pts, gr, ratio, flavour)
+    return dict(cn=cn, ca=ca, ten=ten, gr=gr, pts=new_pts)
