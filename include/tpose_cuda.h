@@ -1,0 +1,165 @@
+/*
+ * tpose_cuda.h -- C ABI of the B200 (sm_100a) implementation of t-pose's
+ * data-parallel hot path.  Plain pointers and sizes only; every entry point
+ * returns 0 on success or a negative tpose_cuda_status, never exits the
+ * process.  One context = one device + one stream; a context is not thread
+ * safe, distinct contexts are independent.  Host buffers are owned by the
+ * caller, device buffers by the context.
+ *
+ * The reference has no FFI: its "device interface" is the set of TinyEngine
+ * Buffer / Shader / Compute calls made by four lambdas in each program.  Each
+ * entry point below names the reference lines it replaces (paths relative to
+ * the reference repository root).
+ *
+ * Buffer layouts are the reference's SSBO layouts (software/triangulate/
+ * main.cpp:84-101): row k*NT+t of cn/ca/ten is variant k (0 = base, 1+4j+s =
+ * vertex j moved by (+dp,0),(-dp,0),(0,+dp),(0,-dp) for s = 0..3) of triangle t.
+ */
+#ifndef TPOSE_CUDA_H
+#define TPOSE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tpose_cuda_ctx tpose_cuda_ctx;
+
+typedef enum {
+    TPOSE_OK = 0,
+    TPOSE_ERR_ARG = -1,       /* bad argument (sizes, slot, null pointer) */
+    TPOSE_ERR_CUDA = -2,      /* a CUDA runtime call failed; see last_error */
+    TPOSE_ERR_CAPACITY = -3,  /* NT / NP / image exceed what the context was created for */
+    TPOSE_ERR_STATE = -4,     /* call order: no image / no mesh uploaded yet */
+    TPOSE_ERR_NODEVICE = -5   /* no usable CUDA device: there is NO CPU fallback */
+} tpose_cuda_status;
+
+enum { TPOSE_TRIANGULATE = 0, TPOSE_WARP = 1 };          /* shader flavour */
+enum { TPOSE_IMAGE_A = 0, TPOSE_IMAGE_B = 1 };           /* texture slot   */
+
+/* trigger bits reported by tpose_cuda_run */
+enum {
+    TPOSE_TRIG_CONVERGED = 1u,  /* |relerr| < rel_tol (triangulation.hpp:653-674) */
+    TPOSE_TRIG_MAXSTEPS  = 2u
+};
+
+/* Limits of the packed row-prefix table: */
+#define TPOSE_MAX_WIDTH  4095
+#define TPOSE_MAX_HEIGHT 8192
+/* The reference allocates 2<<18 elements per SSBO and indexes 13*NT of them
+ * (source/triangulation.hpp:97,592-601): NT <= 40329. */
+#define TPOSE_REF_MAXT (2 << 18)
+
+/* ---- lifetime ---------------------------------------------------------- */
+
+/* Replaces tpose::init() (source/triangulation.hpp:592-608): allocates the
+ * device buffers.  `stream` is a cudaStream_t to run on (NULL = the context
+ * creates its own non-blocking stream). */
+int tpose_cuda_create(int device, int max_triangles, int max_points, void *stream,
+                      tpose_cuda_ctx **out);
+/* Replaces tpose::quit() (source/triangulation.hpp:610-626). */
+int tpose_cuda_destroy(tpose_cuda_ctx *ctx);
+/* Message of the last failing call on this context ("" if none). NULL ctx:
+ * message of the last failing tpose_cuda_create. */
+const char *tpose_cuda_last_error(const tpose_cuda_ctx *ctx);
+/* Library version / build string (arch, compiler). */
+const char *tpose_cuda_version(void);
+
+/* ---- inputs ------------------------------------------------------------ */
+
+/* Replaces `Texture tex(IMG)` (software/triangulate/main.cpp:74,
+ * software/warp/main.cpp:118-119).  rgba: h*w*4 bytes, row 0 = top row.
+ * raster_w x raster_h is the window the reference would open
+ * (Tiny::window(w/1.5, h/1.5), triangulate/main.cpp:53); pass w,h for the
+ * native raster.  Copies the image to the device and builds the row-prefix
+ * moment table the step kernels integrate over. */
+int tpose_cuda_set_image(tpose_cuda_ctx *ctx, int slot, const uint8_t *rgba_host,
+                         int w, int h, int raster_w, int raster_h);
+/* Same, source already on the device (same layout). */
+int tpose_cuda_set_image_device(tpose_cuda_ctx *ctx, int slot, const uint8_t *rgba_dev,
+                                int w, int h, int raster_w, int raster_h);
+
+/* Replaces tpose::upload(tr, uploadcolor) (source/triangulation.hpp:628-643):
+ * pts_xy = NP vec2, tri_xyzw = NT ivec4 (w ignored).  colors_rgba (NT ivec4)
+ * non-NULL == uploadcolor: replicated into all 13 variant rows of `ca`.
+ * ratio = tpose::RATIO (the RATIO uniform of every shader). */
+int tpose_cuda_upload(tpose_cuda_ctx *ctx, const float *pts_xy, int np,
+                      const int32_t *tri_xyzw, int nt,
+                      const int32_t *colors_rgba, float ratio);
+/* pointbuf->fill(points) alone (positions changed, topology did not). */
+int tpose_cuda_upload_points(tpose_cuda_ctx *ctx, const float *pts_xy, int np);
+
+/* ---- the three lambdas, literally --------------------------------------- */
+
+/* computecolors() (triangulate/main.cpp:121-130) / doreset() (warp/main.cpp:
+ * 140-151): draw of 13*NT instances in mode 0.  Triangulate flavour: cn and
+ * ca.rgb of every variant; warp flavour: cn only, ca keeps the upload. */
+int tpose_cuda_colors(tpose_cuda_ctx *ctx, int slot, int flavour);
+/* doenergy() (triangulate/main.cpp:132-141, warp/main.cpp:153-164): draw in
+ * mode 1.  ten of every variant from the stored cn/ca; zeroes gr. */
+int tpose_cuda_energy(tpose_cuda_ctx *ctx, int slot, int flavour);
+/* doshift() (triangulate/main.cpp:143-155, warp/main.cpp:166-178):
+ * gradient.cs then shift.cs. */
+int tpose_cuda_shift(tpose_cuda_ctx *ctx, int flavour);
+
+/* ---- fused path --------------------------------------------------------- */
+
+/* `nsteps` frames at frozen topology with no host round trip:
+ *   triangulate: { mode 0, mode 1, gradient, shift } at the current points
+ *   warp:        { doreset, doenergy, doshift }
+ * which is the per-frame device work of triangulate/main.cpp:196-197 +
+ * :180-184 and warp/main.cpp:220-222.  After the call cn/ca/ten hold the
+ * values of the LAST evaluated positions and the points are the shifted ones,
+ * i.e. exactly what the reference reads back at main.cpp:201-204. */
+int tpose_cuda_step(tpose_cuda_ctx *ctx, int slot, int flavour, int nsteps);
+
+/* Up to `max_steps` frames, stopping after the first one whose geterr value
+ * (float32 running sum of the base energies, relative change against the
+ * previous sum -- source/triangulation.hpp:653-674) is < rel_tol.  The running
+ * `toterr` lives in the context (it is a global in the reference, starts at 1
+ * and persists across levels); tpose_cuda_set_toterr overrides it.
+ * steps_done / trigger_flags / last_err (|relerr| of the last frame) may be NULL. */
+int tpose_cuda_run(tpose_cuda_ctx *ctx, int slot, int flavour, int max_steps, float rel_tol,
+                   int *steps_done, uint32_t *trigger_flags, float *last_err);
+int tpose_cuda_set_toterr(tpose_cuda_ctx *ctx, float toterr);
+int tpose_cuda_get_toterr(tpose_cuda_ctx *ctx, float *toterr);
+
+/* ---- read back ---------------------------------------------------------- */
+
+/* Buffer::retrieve of tenergybuf / tcolnumbuf / tcolaccbuf / pointbuf
+ * (triangulate/main.cpp:201-204,221).  Any pointer may be NULL.
+ * ten13, cn13: 13*NT int32; ca13_rgba: 13*NT ivec4; pts_xy: NP vec2. */
+int tpose_cuda_retrieve(tpose_cuda_ctx *ctx, int32_t *ten13, int32_t *cn13,
+                        int32_t *ca13_rgba, float *pts_xy);
+/* Only the base rows (what geterr / maxerrid / the flip set read): NT each. */
+int tpose_cuda_retrieve_base(tpose_cuda_ctx *ctx, int32_t *ten, int32_t *cn, int32_t *ca_rgba);
+/* pgradbuf: NP ivec2 (debug / parity). */
+int tpose_cuda_retrieve_gradient(tpose_cuda_ctx *ctx, int32_t *gr_xy);
+
+/* Per-pixel triangle-ID raster of the NT base instances at the current
+ * points, raster_h*raster_w int32, -1 where nothing is drawn; where instances
+ * overlap the highest index (last drawn) wins.  This is what mode 2 of
+ * triangle.fs displays (triangulate/main.cpp:157-166). */
+int tpose_cuda_raster_ids(tpose_cuda_ctx *ctx, int slot, int32_t *ids_host);
+
+/* Device time in milliseconds of the most recent step/run call on this
+ * context, measured with CUDA events on the context's stream. */
+int tpose_cuda_last_elapsed_ms(tpose_cuda_ctx *ctx, float *ms);
+/* Block until the context's stream is idle. */
+int tpose_cuda_sync(tpose_cuda_ctx *ctx);
+/* Number of kernel launches issued by this context so far. */
+int64_t tpose_cuda_launch_count(const tpose_cuda_ctx *ctx);
+
+/* Page-locked host memory for the buffers handed to set_image / upload / retrieve
+ * (optional: pageable pointers work, pinned ones copy faster). */
+int tpose_cuda_host_alloc(size_t bytes, void **out);
+int tpose_cuda_host_free(void *p);
+/* Writes `bytes` of device scratch owned by the context (benchmark hygiene: evicts L2). */
+int tpose_cuda_flush_l2(tpose_cuda_ctx *ctx, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPOSE_CUDA_H */

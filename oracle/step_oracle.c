@@ -32,7 +32,7 @@
  *   - window transform in float32, one rounding per operation, no FMA:
  *        xn = (p.x + Dx) / RATIO ; yn = p.y + Dy
  *        xw = xn*(0.5f*W) + 0.5f*W ; yw = yn*(0.5f*H) + 0.5f*H   (y up)
- *   - snap to 1/256 pixel: X = lrintf(clamp(xw, +-2^21) * 256), same for y,
+ *   - snap to 1/256 pixel: X = lrintf(clamp(xw, +-2^15) * 256), same for y,
  *     then flip to y-down: Y = 256*H - Yup;
  *   - coverage: exact int64 edge functions, top-left fill rule in the y-down
  *     frame, both windings rasterise (glDisable(GL_CULL_FACE),
@@ -63,7 +63,7 @@ float tpo_dp(int NT, int flavour)
 
 static int32_t snap256(float w)
 {
-    const float lim = 2097152.0f;
+    const float lim = 32768.0f;
     w = fminf(fmaxf(w, -lim), lim);
     return (int32_t)lrintf(w * 256.0f);
 }

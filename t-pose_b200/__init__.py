@@ -1,0 +1,200 @@
+"""tpose_b200 -- Python front end (ctypes) of libtpose_cuda.so, the sm_100a implementation of
+t-pose's optimisation step.  The directory name carries a hyphen, so load it with
+`__graft_entry__.load_package()` (importlib) rather than `import`.
+
+This module is glue only: every number comes from the CUDA library.  If the library is missing
+or there is no CUDA device it raises -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtpose_cuda.so")
+
+TRIANGULATE, WARP = 0, 1
+IMAGE_A, IMAGE_B = 0, 1
+TRIG_CONVERGED, TRIG_MAXSTEPS = 1, 2
+
+_lib = None
+
+
+class TposeCudaError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", _HERE, "libtpose_cuda.so"], stdout=out, stderr=out)
+    return LIB_PATH
+
+
+EXPORTS = [
+    "tpose_cuda_create", "tpose_cuda_destroy", "tpose_cuda_last_error", "tpose_cuda_version",
+    "tpose_cuda_set_image", "tpose_cuda_set_image_device", "tpose_cuda_upload",
+    "tpose_cuda_upload_points", "tpose_cuda_colors", "tpose_cuda_energy", "tpose_cuda_shift",
+    "tpose_cuda_step", "tpose_cuda_run", "tpose_cuda_set_toterr", "tpose_cuda_get_toterr",
+    "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
+    "tpose_cuda_raster_ids", "tpose_cuda_last_elapsed_ms", "tpose_cuda_sync",
+    "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TposeCudaError(f"{LIB_PATH} is not built; run __graft_entry__.build() "
+                                 "(there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.tpose_cuda_last_error.restype = C.c_char_p
+        _lib.tpose_cuda_last_error.argtypes = [C.c_void_p]
+        _lib.tpose_cuda_version.restype = C.c_char_p
+        _lib.tpose_cuda_launch_count.restype = C.c_int64
+        _lib.tpose_cuda_launch_count.argtypes = [C.c_void_p]
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One device + one stream; mirrors the call sequence of the reference's lambdas."""
+
+    def __init__(self, device=0, max_triangles=40000, max_points=24000, stream=None):
+        self._h = C.c_void_p()
+        rc = lib().tpose_cuda_create(C.c_int(device), C.c_int(max_triangles), C.c_int(max_points),
+                                     C.c_void_p(stream or 0), C.byref(self._h))
+        if rc != 0:
+            msg = lib().tpose_cuda_last_error(None).decode()
+            self._h = None
+            raise TposeCudaError(f"tpose_cuda_create -> {rc}: {msg}")
+        self.NT = self.NP = 0
+        self.shape = [None, None]
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TposeCudaError(f"status {rc}: {lib().tpose_cuda_last_error(self._h).decode()}")
+
+    def close(self):
+        if self._h:
+            lib().tpose_cuda_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- inputs
+    def set_image(self, slot, rgba, raster=None):
+        rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+        h, w = rgba.shape[:2]
+        assert rgba.shape[2] == 4
+        rw, rh = (w, h) if raster is None else raster
+        self._ck(lib().tpose_cuda_set_image(self._h, slot, _ptr(rgba), w, h, rw, rh))
+        self.shape[slot] = (rh, rw)
+
+    def set_image_device(self, slot, dev_ptr, w, h, raster=None):
+        rw, rh = (w, h) if raster is None else raster
+        self._ck(lib().tpose_cuda_set_image_device(self._h, slot, C.c_void_p(dev_ptr), w, h, rw, rh))
+        self.shape[slot] = (rh, rw)
+
+    def upload(self, pts, tri, ratio, colors=None):
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        tri = np.ascontiguousarray(tri, dtype=np.int32)
+        col = None if colors is None else np.ascontiguousarray(colors, dtype=np.int32)
+        assert tri.ndim == 2 and tri.shape[1] == 4 and pts.shape[1] == 2
+        self._ck(lib().tpose_cuda_upload(self._h, _ptr(pts), pts.shape[0], _ptr(tri), tri.shape[0],
+                                         _ptr(col), C.c_float(ratio)))
+        self.NP, self.NT = pts.shape[0], tri.shape[0]
+
+    def upload_points(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        self._ck(lib().tpose_cuda_upload_points(self._h, _ptr(pts), pts.shape[0]))
+
+    # -- the lambdas
+    def colors(self, slot, flavour):
+        self._ck(lib().tpose_cuda_colors(self._h, slot, flavour))
+
+    def energy(self, slot, flavour):
+        self._ck(lib().tpose_cuda_energy(self._h, slot, flavour))
+
+    def shift(self, flavour):
+        self._ck(lib().tpose_cuda_shift(self._h, flavour))
+
+    # -- fused
+    def step(self, slot, flavour, nsteps=1):
+        self._ck(lib().tpose_cuda_step(self._h, slot, flavour, nsteps))
+
+    def run(self, slot, flavour, max_steps, rel_tol):
+        n, f, e = C.c_int(), C.c_uint32(), C.c_float()
+        self._ck(lib().tpose_cuda_run(self._h, slot, flavour, max_steps, C.c_float(rel_tol),
+                                      C.byref(n), C.byref(f), C.byref(e)))
+        return n.value, f.value, e.value
+
+    def set_toterr(self, v):
+        self._ck(lib().tpose_cuda_set_toterr(self._h, C.c_float(v)))
+
+    def get_toterr(self):
+        v = C.c_float()
+        self._ck(lib().tpose_cuda_get_toterr(self._h, C.byref(v)))
+        return v.value
+
+    # -- read back
+    def retrieve(self, ten=True, cn=True, ca=True, pts=True):
+        nv = 13 * self.NT
+        a_ten = np.empty(nv, np.int32) if ten else None
+        a_cn = np.empty(nv, np.int32) if cn else None
+        a_ca = np.empty((nv, 4), np.int32) if ca else None
+        a_pts = np.empty((self.NP, 2), np.float32) if pts else None
+        self._ck(lib().tpose_cuda_retrieve(self._h, _ptr(a_ten), _ptr(a_cn), _ptr(a_ca), _ptr(a_pts)))
+        return dict(ten=a_ten, cn=a_cn, ca=a_ca, pts=a_pts)
+
+    def retrieve_base(self):
+        ten = np.empty(self.NT, np.int32)
+        cn = np.empty(self.NT, np.int32)
+        ca = np.empty((self.NT, 4), np.int32)
+        self._ck(lib().tpose_cuda_retrieve_base(self._h, _ptr(ten), _ptr(cn), _ptr(ca)))
+        return ten, cn, ca
+
+    def retrieve_gradient(self):
+        gr = np.empty((self.NP, 2), np.int32)
+        self._ck(lib().tpose_cuda_retrieve_gradient(self._h, _ptr(gr)))
+        return gr
+
+    def raster_ids(self, slot=0):
+        h, w = self.shape[slot]
+        ids = np.empty((h, w), np.int32)
+        self._ck(lib().tpose_cuda_raster_ids(self._h, slot, _ptr(ids)))
+        return ids
+
+    def last_elapsed_ms(self):
+        ms = C.c_float()
+        self._ck(lib().tpose_cuda_last_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self._ck(lib().tpose_cuda_sync(self._h))
+
+    def launch_count(self):
+        return int(lib().tpose_cuda_launch_count(self._h))
+
+    def flush_l2(self, nbytes=256 << 20):
+        self._ck(lib().tpose_cuda_flush_l2(self._h, C.c_size_t(nbytes)))
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over page-locked host memory (cudaHostAlloc); keep the returned array alive."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    rc = lib().tpose_cuda_host_alloc(C.c_size_t(max(n, 1)), C.byref(p))
+    if rc != 0:
+        raise TposeCudaError("cudaHostAlloc failed")
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

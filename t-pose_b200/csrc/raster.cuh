@@ -1,0 +1,47 @@
+// raster.cuh -- per-pixel triangle-ID raster of the NT base instances (what mode 2 of
+// software/triangulate/shader/triangle.fs:46-50 shows, and what the fragment stage iterates
+// over in modes 0/1).  One warp per triangle: rows in sequence, lanes across the span, so the
+// stores of a row are coalesced.  Overlaps resolve to the highest instance index (draw order).
+#pragma once
+#include "common.cuh"
+
+namespace tpose_dev {
+
+__global__ void __launch_bounds__(256)
+k_raster_ids(const float2* __restrict__ pts, const int4* __restrict__ tri, int NT,
+             float ratio, int W, int H, int* __restrict__ ids)
+{
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= NT) return;
+    const int4 tv = tri[t];
+    Xform xf{ratio, 0.5f * (float)W, 0.5f * (float)H, 256 * H};
+    int2 f[3];
+    f[0] = to_fixed(pts[tv.x], 0.0f, 0.0f, xf);
+    f[1] = to_fixed(pts[tv.y], 0.0f, 0.0f, xf);
+    f[2] = to_fixed(pts[tv.z], 0.0f, 0.0f, xf);
+    // every lane walks all three edges row by row (stride 1); a row inside the triangle is
+    // crossed by exactly two of them under the half-open row rule
+    EdgeWalk w[3];
+    int rlo = H, rhi = 0;
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+        w[e].init(f[e], f[(e + 1) % 3], H, 0, 1);
+        if (!w[e].done()) { rlo = min(rlo, w[e].r); rhi = max(rhi, w[e].r_end); }
+    }
+    for (int r = rlo; r < rhi; r++) {
+        int cmin = W, cmax = 0;
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            if (!w[e].done() && w[e].r == r) {
+                const int c = w[e].cross(W);
+                cmin = min(cmin, c); cmax = max(cmax, c);
+                w[e].next(1);
+            }
+        }
+        int* row = ids + (size_t)r * W;
+        for (int x = cmin + lane; x < cmax; x += 32) atomicMax(row + x, t);
+    }
+}
+
+}  // namespace tpose_dev
