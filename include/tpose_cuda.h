@@ -42,7 +42,21 @@ enum { TPOSE_IMAGE_A = 0, TPOSE_IMAGE_B = 1 };           /* texture slot   */
 /* trigger bits reported by tpose_cuda_run */
 enum {
     TPOSE_TRIG_CONVERGED = 1u,  /* |relerr| < rel_tol (triangulation.hpp:653-674) */
-    TPOSE_TRIG_MAXSTEPS  = 2u
+    TPOSE_TRIG_MAXSTEPS  = 2u,  /* max_steps frames done, nothing fired */
+    TPOSE_TRIG_TOPOLOGY  = 4u   /* a per-frame topology edit MAY apply (triangulate/main.cpp:316-346) */
+};
+
+/* The eight SSBO binding points of the reference (software/triangulate/main.cpp:84-101), for
+ * tpose_cuda_read / tpose_cuda_write == Buffer::retrieve / Buffer::fill on that buffer. */
+enum {
+    TPOSE_BUF_POINTS = 0,   /* pointbuf    vec2   NP      */
+    TPOSE_BUF_INDEX = 1,    /* trianglebuf ivec4  NT      */
+    TPOSE_BUF_COLACC = 2,   /* tcolaccbuf  ivec4  13*NT   */
+    TPOSE_BUF_COLNUM = 3,   /* tcolnumbuf  int    13*NT   */
+    TPOSE_BUF_TENERGY = 4,  /* tenergybuf  int    13*NT   */
+    TPOSE_BUF_PENERGY = 5,  /* penergybuf  int    (dead in the reference: lambda = 0; reads as 0) */
+    TPOSE_BUF_GRADIENT = 6, /* pgradbuf    ivec2  NP      */
+    TPOSE_BUF_NRING = 7     /* tnringbuf   int    (never read by the reference; reads as 0) */
 };
 
 /* Limits of the packed row-prefix table: */
@@ -126,6 +140,24 @@ int tpose_cuda_run(tpose_cuda_ctx *ctx, int slot, int flavour, int max_steps, fl
 int tpose_cuda_set_toterr(tpose_cuda_ctx *ctx, float toterr);
 int tpose_cuda_get_toterr(tpose_cuda_ctx *ctx, float *toterr);
 
+/* The topology the HOST currently holds (tr.triangles / tr.halfedges).  The reference edits its
+ * host mesh every frame (prune, flips of angles > 0.8*pi, collapse of edges <= 0.01 --
+ * triangulate/main.cpp:316-346) and uploads it only when prune/collapse/split changed something,
+ * so the host mesh can differ from the uploaded one by pending flips.  With a watch topology set,
+ * tpose_cuda_run also stops (TPOSE_TRIG_TOPOLOGY) after the first frame at whose end one of those
+ * edits could apply -- a conservative superset, decided on the device from the shifted points --
+ * so the caller runs the reference's per-frame host code only on frames where it can do
+ * something.  tri_xyzw == NULL switches the watch off.  halfedges: 3*nt twins or -1. */
+int tpose_cuda_watch(tpose_cuda_ctx *ctx, const int32_t *tri_xyzw, const int32_t *halfedges, int nt);
+
+/* ---- batches of independent jobs --------------------------------------------
+ * n contexts on the same device advance in lock step, one launch per frame for all of them
+ * (blockIdx.y = job).  Jobs are independent problems (own image, mesh, buffers); results are
+ * identical to running each context alone.  Work is issued on ctxs[0]'s stream. */
+int tpose_cuda_batch_step(tpose_cuda_ctx *const *ctxs, int n, const int *slots, int flavour, int nsteps);
+int tpose_cuda_batch_run(tpose_cuda_ctx *const *ctxs, int n, const int *slots, int flavour, int max_steps,
+                         float rel_tol, int *steps_done, uint32_t *trigger_flags);
+
 /* ---- read back ---------------------------------------------------------- */
 
 /* Buffer::retrieve of tenergybuf / tcolnumbuf / tcolaccbuf / pointbuf
@@ -137,6 +169,11 @@ int tpose_cuda_retrieve(tpose_cuda_ctx *ctx, int32_t *ten13, int32_t *cn13,
 int tpose_cuda_retrieve_base(tpose_cuda_ctx *ctx, int32_t *ten, int32_t *cn, int32_t *ca_rgba);
 /* pgradbuf: NP ivec2 (debug / parity). */
 int tpose_cuda_retrieve_gradient(tpose_cuda_ctx *ctx, int32_t *gr_xy);
+
+/* Buffer::retrieve(count, out) / Buffer::fill(count, in) on one binding point, elements
+ * [first, first+count) in that buffer's element type. */
+int tpose_cuda_read(tpose_cuda_ctx *ctx, int buffer, size_t first, size_t count, void *out);
+int tpose_cuda_write(tpose_cuda_ctx *ctx, int buffer, size_t first, size_t count, const void *in);
 
 /* Per-pixel triangle-ID raster of the NT base instances at the current
  * points, raster_h*raster_w int32, -1 where nothing is drawn; where instances

@@ -15,7 +15,11 @@ LIB_PATH = os.path.join(_HERE, "libtpose_cuda.so")
 
 TRIANGULATE, WARP = 0, 1
 IMAGE_A, IMAGE_B = 0, 1
-TRIG_CONVERGED, TRIG_MAXSTEPS = 1, 2
+TRIG_CONVERGED, TRIG_MAXSTEPS, TRIG_TOPOLOGY = 1, 2, 4
+(BUF_POINTS, BUF_INDEX, BUF_COLACC, BUF_COLNUM, BUF_TENERGY, BUF_PENERGY, BUF_GRADIENT,
+ BUF_NRING) = range(8)
+_BUF_DTYPE = {0: (np.float32, 2), 1: (np.int32, 4), 2: (np.int32, 4), 3: (np.int32, 1), 4: (np.int32, 1),
+              5: (np.int32, 1), 6: (np.int32, 2), 7: (np.int32, 1)}
 
 _lib = None
 
@@ -39,6 +43,7 @@ EXPORTS = [
     "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
     "tpose_cuda_raster_ids", "tpose_cuda_last_elapsed_ms", "tpose_cuda_sync",
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
+    "tpose_cuda_watch", "tpose_cuda_read", "tpose_cuda_write", "tpose_cuda_batch_step", "tpose_cuda_batch_run",
 ]
 
 
@@ -137,6 +142,26 @@ class Context:
                                       C.byref(n), C.byref(f), C.byref(e)))
         return n.value, f.value, e.value
 
+    def watch(self, tri=None, halfedges=None):
+        """The host's current topology for the per-frame edit watch (None switches it off)."""
+        if tri is None:
+            self._ck(lib().tpose_cuda_watch(self._h, None, None, 0))
+            return
+        tri = np.ascontiguousarray(tri, dtype=np.int32)
+        he = np.ascontiguousarray(halfedges, dtype=np.int32)
+        self._ck(lib().tpose_cuda_watch(self._h, _ptr(tri), _ptr(he), tri.shape[0]))
+
+    def read(self, which, first, count):
+        dt, width = _BUF_DTYPE[which]
+        out = np.empty((count, width) if width > 1 else (count,), dt)
+        self._ck(lib().tpose_cuda_read(self._h, which, C.c_size_t(first), C.c_size_t(count), _ptr(out)))
+        return out
+
+    def write(self, which, first, data):
+        dt, width = _BUF_DTYPE[which]
+        data = np.ascontiguousarray(data, dtype=dt)
+        self._ck(lib().tpose_cuda_write(self._h, which, C.c_size_t(first), C.c_size_t(data.shape[0]), _ptr(data)))
+
     def set_toterr(self, v):
         self._ck(lib().tpose_cuda_set_toterr(self._h, C.c_float(v)))
 
@@ -186,6 +211,29 @@ class Context:
 
     def flush_l2(self, nbytes=256 << 20):
         self._ck(lib().tpose_cuda_flush_l2(self._h, C.c_size_t(nbytes)))
+
+
+def _handles(ctxs):
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    return arr
+
+
+def batch_step(ctxs, flavour, nsteps=1, slots=None):
+    """nsteps frames of every context in one launch per frame (contexts on one device)."""
+    sl = None if slots is None else (C.c_int * len(ctxs))(*slots)
+    rc = lib().tpose_cuda_batch_step(_handles(ctxs), len(ctxs), sl, flavour, nsteps)
+    if rc != 0:
+        raise TposeCudaError(f"batch_step -> {rc}: {lib().tpose_cuda_last_error(ctxs[0]._h).decode()}")
+
+
+def batch_run(ctxs, flavour, max_steps, rel_tol, slots=None):
+    sl = None if slots is None else (C.c_int * len(ctxs))(*slots)
+    done = (C.c_int * len(ctxs))()
+    trig = (C.c_uint32 * len(ctxs))()
+    rc = lib().tpose_cuda_batch_run(_handles(ctxs), len(ctxs), sl, flavour, max_steps, C.c_float(rel_tol), done, trig)
+    if rc != 0:
+        raise TposeCudaError(f"batch_run -> {rc}: {lib().tpose_cuda_last_error(ctxs[0]._h).decode()}")
+    return list(done), list(trig)
 
 
 def pinned_empty(shape, dtype):

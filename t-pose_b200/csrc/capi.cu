@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <string>
+#include <vector>
 
 using namespace tpose_dev;
 
@@ -31,12 +33,17 @@ struct tpose_cuda_ctx {
     uchar4* staging = nullptr; size_t staging_cap = 0;   // source-resolution upload buffer
     float2* pts = nullptr;
     int4* tri = nullptr;
-    int* cn = nullptr; int4* ca = nullptr; int* ten = nullptr;
+    int* cn[2] = {nullptr, nullptr}; int4* ca[2] = {nullptr, nullptr}; int* ten[2] = {nullptr, nullptr};
+    int cur = 0;                      // buffer set holding the last committed evaluation
     int2* gr = nullptr; int2* gr_acc = nullptr;
-    int* hist = nullptr;
-    unsigned* ticket = nullptr;
-    float* err_state = nullptr;       // [0] toterr [1] |relerr| [2] newerr
-    int* run_state = nullptr;         // [0] stop flag [1] steps done
+    int4* wtri = nullptr; int* whe = nullptr; bool watching = false;
+    unsigned* ticket = nullptr;       // [0] ticket [1] topology trigger accumulator
+    float* err_state = nullptr;       // [0] toterr [1] |relerr| [2] newerr [3] converged flag
+    int* run_state = nullptr;         // RS_STOP, RS_STEPS, RS_TRIG
+    EvalJob* job_dev = nullptr;       // this context's job record (single launches)
+    EvalJob job_host{};               // what job_dev holds
+    bool job_valid = false;
+    EvalJob* batch_jobs = nullptr; int batch_cap = 0;   // job array when this context leads a batch
     int* ids = nullptr; size_t ids_cap = 0;
     unsigned char* flush = nullptr; size_t flush_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -107,22 +114,28 @@ extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, 
 #define ALLOC(ptr, bytes) if ((e = cudaMalloc((void**)&(ptr), (bytes))) != cudaSuccess) return bail("cudaMalloc " #ptr, e)
     ALLOC(ctx->pts, sizeof(float2) * max_points);
     ALLOC(ctx->tri, sizeof(int4) * max_triangles);
-    ALLOC(ctx->cn, sizeof(int) * nv);
-    ALLOC(ctx->ca, sizeof(int4) * nv);
-    ALLOC(ctx->ten, sizeof(int) * nv);
+    for (int s = 0; s < 2; s++) {
+        ALLOC(ctx->cn[s], sizeof(int) * nv);
+        ALLOC(ctx->ca[s], sizeof(int4) * nv);
+        ALLOC(ctx->ten[s], sizeof(int) * nv);
+    }
     ALLOC(ctx->gr, sizeof(int2) * max_points);
     ALLOC(ctx->gr_acc, sizeof(int2) * max_points);
-    ALLOC(ctx->hist, sizeof(int) * max_triangles);
-    ALLOC(ctx->ticket, sizeof(unsigned));
+    ALLOC(ctx->wtri, sizeof(int4) * max_triangles);
+    ALLOC(ctx->whe, sizeof(int) * 3 * max_triangles);
+    ALLOC(ctx->ticket, sizeof(unsigned) * 2);
     ALLOC(ctx->err_state, sizeof(float) * 4);
     ALLOC(ctx->run_state, sizeof(int) * 4);
+    ALLOC(ctx->job_dev, sizeof(EvalJob));
 #undef ALLOC
-    cudaMemsetAsync(ctx->cn, 0, sizeof(int) * nv, ctx->stream);
-    cudaMemsetAsync(ctx->ca, 0, sizeof(int4) * nv, ctx->stream);
-    cudaMemsetAsync(ctx->ten, 0, sizeof(int) * nv, ctx->stream);
+    for (int s = 0; s < 2; s++) {
+        cudaMemsetAsync(ctx->cn[s], 0, sizeof(int) * nv, ctx->stream);
+        cudaMemsetAsync(ctx->ca[s], 0, sizeof(int4) * nv, ctx->stream);
+        cudaMemsetAsync(ctx->ten[s], 0, sizeof(int) * nv, ctx->stream);
+    }
     cudaMemsetAsync(ctx->gr, 0, sizeof(int2) * max_points, ctx->stream);
     cudaMemsetAsync(ctx->gr_acc, 0, sizeof(int2) * max_points, ctx->stream);
-    cudaMemsetAsync(ctx->ticket, 0, sizeof(unsigned), ctx->stream);
+    cudaMemsetAsync(ctx->ticket, 0, sizeof(unsigned) * 2, ctx->stream);
     cudaMemsetAsync(ctx->run_state, 0, sizeof(int) * 4, ctx->stream);
     const float st[4] = {1.0f, 0.0f, 0.0f, 0.0f};   // toterr starts at 1 (triangulation.hpp:648)
     cudaMemcpyAsync(ctx->err_state, st, sizeof st, cudaMemcpyHostToDevice, ctx->stream);
@@ -141,9 +154,11 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->img) { cudaFree(s.rgba); cudaFree(s.table); }
-    cudaFree(ctx->staging); cudaFree(ctx->pts); cudaFree(ctx->tri); cudaFree(ctx->cn); cudaFree(ctx->ca);
-    cudaFree(ctx->ten); cudaFree(ctx->gr); cudaFree(ctx->gr_acc); cudaFree(ctx->hist); cudaFree(ctx->ticket);
+    for (int s = 0; s < 2; s++) { cudaFree(ctx->cn[s]); cudaFree(ctx->ca[s]); cudaFree(ctx->ten[s]); }
+    cudaFree(ctx->staging); cudaFree(ctx->pts); cudaFree(ctx->tri);
+    cudaFree(ctx->gr); cudaFree(ctx->gr_acc); cudaFree(ctx->wtri); cudaFree(ctx->whe); cudaFree(ctx->ticket);
     cudaFree(ctx->err_state); cudaFree(ctx->run_state); cudaFree(ctx->ids); cudaFree(ctx->flush);
+    cudaFree(ctx->job_dev); cudaFree(ctx->batch_jobs);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -226,9 +241,11 @@ extern "C" int tpose_cuda_upload(tpose_cuda_ctx* ctx, const float* pts_xy, int n
     CK(cudaMemcpyAsync(ctx->pts, pts_xy, sizeof(float2) * np, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->tri, tri_xyzw, sizeof(int4) * nt, cudaMemcpyHostToDevice, ctx->stream));
     if (colors_rgba) {   // triangulation.hpp:633-641: every variant row gets the triangle's colour
-        for (int k = 0; k < kVariants; k++)
-            CK(cudaMemcpyAsync(ctx->ca + (size_t)k * nt, colors_rgba, sizeof(int4) * nt, cudaMemcpyHostToDevice, ctx->stream));
+        for (int s = 0; s < 2; s++)
+            for (int k = 0; k < kVariants; k++)
+                CK(cudaMemcpyAsync(ctx->ca[s] + (size_t)k * nt, colors_rgba, sizeof(int4) * nt, cudaMemcpyHostToDevice, ctx->stream));
     }
+    if (nt != ctx->NT) ctx->watching = false;   // a watch topology is only valid for the same NT
     ctx->NT = nt; ctx->NP = np; ctx->ratio = ratio; ctx->have_mesh = true;
     CK(cudaStreamSynchronize(ctx->stream));   // caller may reuse its host buffers
     return TPOSE_OK;
@@ -247,45 +264,73 @@ extern "C" int tpose_cuda_upload_points(tpose_cuda_ctx* ctx, const float* pts_xy
 
 // ---- evaluation -----------------------------------------------------------------------------
 
-static int pick_group(const tpose_cuda_ctx* ctx, int H)
+static int pick_group(const tpose_cuda_ctx* ctx, int NT, int H)
 {
     if (ctx->group == 1 || ctx->group == 2 || ctx->group == 4 || ctx->group == 8 || ctx->group == 16 || ctx->group == 32)
         return ctx->group;
     // mean vertical extent of an edge is about H*sqrt(2/NT)*0.6; aim at <= ~8 rows per lane
-    const float rows = 0.6f * (float)H * sqrtf(2.0f / (float)ctx->NT);
+    const float rows = 0.6f * (float)H * sqrtf(2.0f / (float)NT);
     int g = 1;
     while (g < 32 && rows / g > 8.0f) g <<= 1;
     return g;
 }
 
 template <int G, int TPB>
-static void launch_eval(const EvalParams& p, cudaStream_t st)
+static void launch_eval(const EvalJob* jobs, int njobs, int max_nt, int set, unsigned flags, float tol, cudaStream_t st)
 {
-    constexpr int threads = ((TPB * kEdgeVariants * G + 31) / 32) * 32;
-    const int blocks = (p.NT + TPB - 1) / TPB;
-    k_eval<G, TPB><<<blocks, threads, 0, st>>>(p);
+    const dim3 grid((max_nt + TPB - 1) / TPB, njobs);
+    k_eval<G, TPB><<<grid, EvalCfg<G, TPB>::kThreads, 0, st>>>(jobs, set, flags, tol);
 }
 
-static int eval(tpose_cuda_ctx* ctx, int slot, int flavour, unsigned flags, bool with_stop)
+static void launch_eval_group(int group, const EvalJob* jobs, int njobs, int max_nt, int set, unsigned flags, float tol, cudaStream_t st)
+{
+    switch (group) {
+    case 1: launch_eval<1, 8>(jobs, njobs, max_nt, set, flags, tol, st); break;
+    case 2: launch_eval<2, 4>(jobs, njobs, max_nt, set, flags, tol, st); break;
+    case 4: launch_eval<4, 2>(jobs, njobs, max_nt, set, flags, tol, st); break;
+    case 8: launch_eval<8, 1>(jobs, njobs, max_nt, set, flags, tol, st); break;
+    case 16: launch_eval<16, 1>(jobs, njobs, max_nt, set, flags, tol, st); break;
+    default: launch_eval<32, 1>(jobs, njobs, max_nt, set, flags, tol, st); break;
+    }
+}
+
+// the job record of this context for (slot, flavour)
+static EvalJob make_job(const tpose_cuda_ctx* ctx, int slot, int flavour)
 {
     const ImageSlot& s = ctx->img[slot];
-    EvalParams p;
-    p.table = s.table; p.pitch = s.pitch; p.W = s.W; p.H = s.H;
-    p.pts = ctx->pts; p.tri = ctx->tri; p.NT = ctx->NT; p.NP = ctx->NP;
-    p.ratio = ctx->ratio;
-    p.dp = dp_for(ctx->NT, flavour);
-    p.step = flavour == TPOSE_WARP ? 0.00003f : 0.00005f;
-    p.cn = ctx->cn; p.ca = ctx->ca; p.ten = ctx->ten; p.gr = ctx->gr; p.gr_acc = ctx->gr_acc;
-    p.stop = with_stop ? ctx->run_state : nullptr;
-    p.hist = ctx->hist; p.ticket = ctx->ticket; p.flags = flags;
-    switch (pick_group(ctx, s.H)) {
-    case 1: launch_eval<1, 8>(p, ctx->stream); break;
-    case 2: launch_eval<2, 4>(p, ctx->stream); break;
-    case 4: launch_eval<4, 2>(p, ctx->stream); break;
-    case 8: launch_eval<8, 1>(p, ctx->stream); break;
-    case 16: launch_eval<16, 1>(p, ctx->stream); break;
-    default: launch_eval<32, 1>(p, ctx->stream); break;
+    EvalJob j;
+    memset(&j, 0, sizeof j);
+    j.table = s.table; j.pitch = s.pitch; j.W = s.W; j.H = s.H;
+    j.pts = ctx->pts; j.tri = ctx->tri; j.NT = ctx->NT; j.NP = ctx->NP;
+    j.ratio = ctx->ratio;
+    j.dp = dp_for(ctx->NT, flavour);
+    j.step = flavour == TPOSE_WARP ? 0.00003f : 0.00005f;
+    for (int k = 0; k < 2; k++) { j.cn[k] = ctx->cn[k]; j.ca[k] = ctx->ca[k]; j.ten[k] = ctx->ten[k]; }
+    j.gr = ctx->gr; j.gr_acc = ctx->gr_acc;
+    j.wtri = ctx->watching ? ctx->wtri : nullptr;
+    j.whe = ctx->watching ? ctx->whe : nullptr;
+    j.err_state = ctx->err_state; j.run_state = ctx->run_state;
+    j.trig = ctx->ticket + 1; j.ticket = ctx->ticket;
+    return j;
+}
+
+// make job_dev current (a 200-byte copy, only when something changed)
+static int sync_job(tpose_cuda_ctx* ctx, int slot, int flavour)
+{
+    const EvalJob j = make_job(ctx, slot, flavour);
+    if (!ctx->job_valid || memcmp(&j, &ctx->job_host, sizeof j) != 0) {
+        ctx->job_host = j;
+        CK(cudaMemcpyAsync(ctx->job_dev, &ctx->job_host, sizeof j, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->job_valid = true;
     }
+    return TPOSE_OK;
+}
+
+static int eval(tpose_cuda_ctx* ctx, int slot, int flavour, int set, unsigned flags, float tol = 0.0f)
+{
+    int rc = sync_job(ctx, slot, flavour);
+    if (rc) return rc;
+    launch_eval_group(pick_group(ctx, ctx->NT, ctx->img[slot].H), ctx->job_dev, 1, ctx->NT, set, flags, tol, ctx->stream);
     ctx->launches++;
     CK(cudaGetLastError());
     return TPOSE_OK;
@@ -305,15 +350,15 @@ static int check_ready(tpose_cuda_ctx* ctx, int slot, int flavour)
 static unsigned fused_flags(int flavour)
 {
     return flavour == TPOSE_WARP
-        ? (EV_WRITE_CN | EV_WRITE_TEN | EV_MEAN_STORED | EV_GRAD_SHIFT | EV_HISTORY)
-        : (EV_WRITE_CN | EV_WRITE_CA | EV_WRITE_TEN | EV_MEAN_DIVIDE | EV_GRAD_SHIFT | EV_HISTORY);
+        ? (EV_WRITE_CN | EV_WRITE_TEN | EV_MEAN_STORED | EV_GRAD_SHIFT)
+        : (EV_WRITE_CN | EV_WRITE_CA | EV_WRITE_TEN | EV_MEAN_DIVIDE | EV_GRAD_SHIFT);
 }
 
 extern "C" int tpose_cuda_colors(tpose_cuda_ctx* ctx, int slot, int flavour)
 {
     int rc = check_ready(ctx, slot, flavour);
     if (rc) return rc;
-    return eval(ctx, slot, flavour, flavour == TPOSE_WARP ? EV_WRITE_CN : (EV_WRITE_CN | EV_WRITE_CA), false);
+    return eval(ctx, slot, flavour, ctx->cur, flavour == TPOSE_WARP ? EV_WRITE_CN : (EV_WRITE_CN | EV_WRITE_CA));
 }
 
 extern "C" int tpose_cuda_energy(tpose_cuda_ctx* ctx, int slot, int flavour)
@@ -322,8 +367,8 @@ extern "C" int tpose_cuda_energy(tpose_cuda_ctx* ctx, int slot, int flavour)
     if (rc) return rc;
     k_zero_gradient<<<(ctx->NP + 255) / 256, 256, 0, ctx->stream>>>(ctx->gr, ctx->NP);   // triangle.vs:95-97
     ctx->launches++;
-    const unsigned fl = EV_WRITE_TEN | EV_MEAN_STORED | EV_HISTORY | (flavour == TPOSE_WARP ? 0u : EV_MEAN_DIVIDE);
-    return eval(ctx, slot, flavour, fl, false);
+    const unsigned fl = EV_WRITE_TEN | EV_MEAN_STORED | (flavour == TPOSE_WARP ? 0u : EV_MEAN_DIVIDE);
+    return eval(ctx, slot, flavour, ctx->cur, fl);
 }
 
 extern "C" int tpose_cuda_shift(tpose_cuda_ctx* ctx, int flavour)
@@ -331,7 +376,7 @@ extern "C" int tpose_cuda_shift(tpose_cuda_ctx* ctx, int flavour)
     if (!ctx) return TPOSE_ERR_ARG;
     if (!ctx->have_mesh) return fail(ctx, TPOSE_ERR_STATE, "no mesh uploaded");
     CK(cudaSetDevice(ctx->device));
-    k_gradient<<<(ctx->NT + 127) / 128, 128, 0, ctx->stream>>>(ctx->tri, ctx->NT, ctx->ten, ctx->gr);
+    k_gradient<<<(ctx->NT + 127) / 128, 128, 0, ctx->stream>>>(ctx->tri, ctx->NT, ctx->ten[ctx->cur], ctx->gr);
     k_shift<<<(ctx->NP + 127) / 128, 128, 0, ctx->stream>>>(ctx->pts, ctx->NP, ctx->gr, ctx->ratio,
                                                             flavour == TPOSE_WARP ? 0.00003f : 0.00005f);
     ctx->launches += 2;
@@ -344,14 +389,32 @@ extern "C" int tpose_cuda_step(tpose_cuda_ctx* ctx, int slot, int flavour, int n
     int rc = check_ready(ctx, slot, flavour);
     if (rc) return rc;
     if (nsteps < 0) return fail(ctx, TPOSE_ERR_ARG, "step: nsteps < 0");
+    rc = sync_job(ctx, slot, flavour);
+    if (rc) return rc;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     const unsigned fl = fused_flags(flavour);
     for (int i = 0; i < nsteps; i++) {
-        rc = eval(ctx, slot, flavour, fl, false);
+        ctx->cur ^= 1;
+        rc = eval(ctx, slot, flavour, ctx->cur, fl);
         if (rc) return rc;
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     return TPOSE_OK;
+}
+
+// Launch j evaluates the points after j shifts into set (first+j)&1 and carries the checks of frame
+// j-1; launch max_steps is check-only.  See eval.cuh.
+static void issue_run(tpose_cuda_ctx* lead, const EvalJob* jobs, int njobs, int max_nt, int group, int first_set,
+                      int flavour, int max_steps, float rel_tol)
+{
+    const unsigned fl = fused_flags(flavour) | EV_HONOUR_STOP;
+    for (int j = 0; j <= max_steps; j++) {
+        unsigned f = fl;
+        if (j > 0) f |= EV_CHECK_PREV;
+        if (j == max_steps) f |= EV_FINAL;
+        launch_eval_group(group, jobs, njobs, max_nt, (first_set + j) & 1, f, rel_tol, lead->stream);
+        lead->launches++;
+    }
 }
 
 extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int max_steps, float rel_tol,
@@ -359,23 +422,22 @@ extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int ma
 {
     int rc = check_ready(ctx, slot, flavour);
     if (rc) return rc;
-    if (max_steps < 0) return fail(ctx, TPOSE_ERR_ARG, "run: max_steps < 0");
+    if (max_steps < 1) return fail(ctx, TPOSE_ERR_ARG, "run: max_steps < 1");
+    rc = sync_job(ctx, slot, flavour);
+    if (rc) return rc;
     CK(cudaMemsetAsync(ctx->run_state, 0, sizeof(int) * 4, ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    const unsigned fl = fused_flags(flavour);
-    for (int i = 0; i < max_steps; i++) {
-        rc = eval(ctx, slot, flavour, fl, true);
-        if (rc) return rc;
-        k_geterr<<<1, 32, 0, ctx->stream>>>(ctx->hist, ctx->NT, ctx->err_state, rel_tol, ctx->run_state, ctx->run_state + 1);
-        ctx->launches++;
-    }
+    const int first = ctx->cur ^ 1;
+    issue_run(ctx, ctx->job_dev, 1, ctx->NT, pick_group(ctx, ctx->NT, ctx->img[slot].H), first, flavour, max_steps, rel_tol);
+    CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     int rs[4]; float es[4];
     CK(cudaMemcpyAsync(rs, ctx->run_state, sizeof rs, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(es, ctx->err_state, sizeof es, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (steps_done) *steps_done = rs[1];
-    if (trigger_flags) *trigger_flags = rs[0] ? TPOSE_TRIG_CONVERGED : TPOSE_TRIG_MAXSTEPS;
+    if (rs[RS_STEPS] > 0) ctx->cur = (first + rs[RS_STEPS] - 1) & 1;
+    if (steps_done) *steps_done = rs[RS_STEPS];
+    if (trigger_flags) *trigger_flags = (uint32_t)rs[RS_TRIG];
     if (last_err) *last_err = es[1];
     return TPOSE_OK;
 }
@@ -398,6 +460,115 @@ extern "C" int tpose_cuda_get_toterr(tpose_cuda_ctx* ctx, float* toterr)
     return TPOSE_OK;
 }
 
+extern "C" int tpose_cuda_watch(tpose_cuda_ctx* ctx, const int32_t* tri_xyzw, const int32_t* halfedges, int nt)
+{
+    if (!ctx) return TPOSE_ERR_ARG;
+    if (!tri_xyzw) { ctx->watching = false; return TPOSE_OK; }
+    if (!ctx->have_mesh) return fail(ctx, TPOSE_ERR_STATE, "watch: no mesh uploaded");
+    if (!halfedges || nt != ctx->NT) return fail(ctx, TPOSE_ERR_ARG, "watch: needs halfedges and the uploaded mesh's NT");
+    for (int t = 0; t < nt; t++)
+        for (int k = 0; k < 3; k++) {
+            const int v = tri_xyzw[4 * t + k], h = halfedges[3 * t + k];
+            if (v < 0 || v >= ctx->NP || h < -1 || h >= 3 * nt) return fail(ctx, TPOSE_ERR_ARG, "watch: index out of range");
+        }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->wtri, tri_xyzw, sizeof(int4) * nt, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->whe, halfedges, sizeof(int) * 3 * nt, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->watching = true;
+    return TPOSE_OK;
+}
+
+// ---- batches ---------------------------------------------------------------------------------
+
+static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, int flavour, int* max_nt, int* group)
+{
+    if (!ctxs || n < 1 || !ctxs[0]) return TPOSE_ERR_ARG;
+    tpose_cuda_ctx* lead = ctxs[0];
+    tpose_cuda_ctx* ctx = lead;   // for CK
+    std::vector<EvalJob> jobs((size_t)n);
+    int mx = 0; double rows = 0.0;
+    for (int i = 0; i < n; i++) {
+        const int slot = slots ? slots[i] : 0;
+        int rc = check_ready(ctxs[i], slot, flavour);
+        if (rc) { if (ctxs[i] && ctxs[i] != lead) lead->err = "batch: job " + std::to_string(i) + ": " + ctxs[i]->err; return rc; }
+        if (ctxs[i]->device != lead->device) return fail(lead, TPOSE_ERR_ARG, "batch: contexts live on different devices");
+        for (int k = 0; k < i; k++) if (ctxs[k] == ctxs[i]) return fail(lead, TPOSE_ERR_ARG, "batch: a context appears twice");
+        if (ctxs[i] != lead) cudaStreamSynchronize(ctxs[i]->stream);   // its uploads are done before we touch its buffers
+        jobs[(size_t)i] = make_job(ctxs[i], slot, flavour);
+        mx = ctxs[i]->NT > mx ? ctxs[i]->NT : mx;
+        rows += 0.6 * ctxs[i]->img[slot].H * sqrt(2.0 / ctxs[i]->NT);
+    }
+    if (lead->batch_cap < n) {
+        cudaFree(lead->batch_jobs); lead->batch_jobs = nullptr; lead->batch_cap = 0;
+        CK(cudaMalloc((void**)&lead->batch_jobs, sizeof(EvalJob) * n));
+        lead->batch_cap = n;
+    }
+    CK(cudaMemcpyAsync(lead->batch_jobs, jobs.data(), sizeof(EvalJob) * n, cudaMemcpyHostToDevice, lead->stream));
+    CK(cudaStreamSynchronize(lead->stream));   // `jobs` is a local
+    *max_nt = mx;
+    int g = lead->group;
+    if (!(g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32)) {
+        g = 1;
+        while (g < 32 && rows / n / g > 8.0) g <<= 1;
+    }
+    *group = g;
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_batch_step(tpose_cuda_ctx* const* ctxs, int n, const int* slots, int flavour, int nsteps)
+{
+    int max_nt = 0, group = 1;
+    int rc = batch_prepare(ctxs, n, slots, flavour, &max_nt, &group);
+    if (rc) return rc;
+    tpose_cuda_ctx* ctx = ctxs[0];
+    if (nsteps < 0) return fail(ctx, TPOSE_ERR_ARG, "batch_step: nsteps < 0");
+    // all jobs must write the same set parity: bring every context to the leader's
+    for (int i = 1; i < n; i++)
+        if (ctxs[i]->cur != ctx->cur) return fail(ctx, TPOSE_ERR_STATE, "batch: contexts are out of step (mix of stepped and fresh contexts)");
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    const unsigned fl = fused_flags(flavour);
+    int cur = ctx->cur;
+    for (int s = 0; s < nsteps; s++) {
+        cur ^= 1;
+        launch_eval_group(group, ctx->batch_jobs, n, max_nt, cur, fl, 0.0f, ctx->stream);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    for (int i = 0; i < n; i++) ctxs[i]->cur = cur;
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_batch_run(tpose_cuda_ctx* const* ctxs, int n, const int* slots, int flavour, int max_steps,
+                                    float rel_tol, int* steps_done, uint32_t* trigger_flags)
+{
+    int max_nt = 0, group = 1;
+    int rc = batch_prepare(ctxs, n, slots, flavour, &max_nt, &group);
+    if (rc) return rc;
+    tpose_cuda_ctx* ctx = ctxs[0];
+    if (max_steps < 1) return fail(ctx, TPOSE_ERR_ARG, "batch_run: max_steps < 1");
+    for (int i = 1; i < n; i++)
+        if (ctxs[i]->cur != ctx->cur) return fail(ctx, TPOSE_ERR_STATE, "batch: contexts are out of step");
+    for (int i = 0; i < n; i++) CK(cudaMemsetAsync(ctxs[i]->run_state, 0, sizeof(int) * 4, ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    const int first = ctx->cur ^ 1;
+    issue_run(ctx, ctx->batch_jobs, n, max_nt, group, first, flavour, max_steps, rel_tol);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    std::vector<int> rs((size_t)4 * n);
+    for (int i = 0; i < n; i++)
+        CK(cudaMemcpyAsync(&rs[(size_t)4 * i], ctxs[i]->run_state, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++) {
+        const int done = rs[(size_t)4 * i + RS_STEPS];
+        if (done > 0) ctxs[i]->cur = (first + done - 1) & 1;
+        if (steps_done) steps_done[i] = done;
+        if (trigger_flags) trigger_flags[i] = (uint32_t)rs[(size_t)4 * i + RS_TRIG];
+    }
+    return TPOSE_OK;
+}
+
 // ---- read back ------------------------------------------------------------------------------
 
 extern "C" int tpose_cuda_retrieve(tpose_cuda_ctx* ctx, int32_t* ten13, int32_t* cn13, int32_t* ca13, float* pts_xy)
@@ -406,9 +577,10 @@ extern "C" int tpose_cuda_retrieve(tpose_cuda_ctx* ctx, int32_t* ten13, int32_t*
     if (!ctx->have_mesh) return fail(ctx, TPOSE_ERR_STATE, "retrieve: no mesh uploaded");
     CK(cudaSetDevice(ctx->device));
     const size_t nv = (size_t)kVariants * ctx->NT;
-    if (ten13) CK(cudaMemcpyAsync(ten13, ctx->ten, sizeof(int) * nv, cudaMemcpyDeviceToHost, ctx->stream));
-    if (cn13) CK(cudaMemcpyAsync(cn13, ctx->cn, sizeof(int) * nv, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ca13) CK(cudaMemcpyAsync(ca13, ctx->ca, sizeof(int4) * nv, cudaMemcpyDeviceToHost, ctx->stream));
+    const int c = ctx->cur;
+    if (ten13) CK(cudaMemcpyAsync(ten13, ctx->ten[c], sizeof(int) * nv, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cn13) CK(cudaMemcpyAsync(cn13, ctx->cn[c], sizeof(int) * nv, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ca13) CK(cudaMemcpyAsync(ca13, ctx->ca[c], sizeof(int4) * nv, cudaMemcpyDeviceToHost, ctx->stream));
     if (pts_xy) CK(cudaMemcpyAsync(pts_xy, ctx->pts, sizeof(float2) * ctx->NP, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return TPOSE_OK;
@@ -420,9 +592,10 @@ extern "C" int tpose_cuda_retrieve_base(tpose_cuda_ctx* ctx, int32_t* ten, int32
     if (!ctx->have_mesh) return fail(ctx, TPOSE_ERR_STATE, "retrieve_base: no mesh uploaded");
     CK(cudaSetDevice(ctx->device));
     const size_t n = (size_t)ctx->NT;
-    if (ten) CK(cudaMemcpyAsync(ten, ctx->ten, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (cn) CK(cudaMemcpyAsync(cn, ctx->cn, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ca) CK(cudaMemcpyAsync(ca, ctx->ca, sizeof(int4) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    const int c = ctx->cur;
+    if (ten) CK(cudaMemcpyAsync(ten, ctx->ten[c], sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cn) CK(cudaMemcpyAsync(cn, ctx->cn[c], sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ca) CK(cudaMemcpyAsync(ca, ctx->ca[c], sizeof(int4) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return TPOSE_OK;
 }
@@ -433,6 +606,53 @@ extern "C" int tpose_cuda_retrieve_gradient(tpose_cuda_ctx* ctx, int32_t* gr_xy)
     if (!ctx->have_mesh) return fail(ctx, TPOSE_ERR_STATE, "retrieve_gradient: no mesh uploaded");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(gr_xy, ctx->gr, sizeof(int2) * ctx->NP, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TPOSE_OK;
+}
+
+// element size, capacity (elements) and device address of one binding point
+static bool buffer_info(tpose_cuda_ctx* ctx, int which, size_t* elem, size_t* cap, void** dev)
+{
+    const size_t nv = (size_t)kVariants * ctx->maxT;
+    const int c = ctx->cur;
+    switch (which) {
+    case TPOSE_BUF_POINTS:   *elem = sizeof(float2); *cap = ctx->maxP; *dev = ctx->pts; return true;
+    case TPOSE_BUF_INDEX:    *elem = sizeof(int4);   *cap = ctx->maxT; *dev = ctx->tri; return true;
+    case TPOSE_BUF_COLACC:   *elem = sizeof(int4);   *cap = nv; *dev = ctx->ca[c]; return true;
+    case TPOSE_BUF_COLNUM:   *elem = sizeof(int);    *cap = nv; *dev = ctx->cn[c]; return true;
+    case TPOSE_BUF_TENERGY:  *elem = sizeof(int);    *cap = nv; *dev = ctx->ten[c]; return true;
+    case TPOSE_BUF_GRADIENT: *elem = sizeof(int2);   *cap = ctx->maxP; *dev = ctx->gr; return true;
+    case TPOSE_BUF_PENERGY:
+    case TPOSE_BUF_NRING:    *elem = sizeof(int);    *cap = (size_t)TPOSE_REF_MAXT; *dev = nullptr; return true;
+    default: return false;
+    }
+}
+
+extern "C" int tpose_cuda_read(tpose_cuda_ctx* ctx, int which, size_t first, size_t count, void* out)
+{
+    if (!ctx) return TPOSE_ERR_ARG;
+    size_t elem, cap; void* dev;
+    if (!out || !buffer_info(ctx, which, &elem, &cap, &dev)) return fail(ctx, TPOSE_ERR_ARG, "read: bad buffer or null output");
+    if (first + count > cap) return fail(ctx, TPOSE_ERR_CAPACITY, "read: range exceeds the buffer");
+    if (count == 0) return TPOSE_OK;
+    if (!dev) { memset(out, 0, elem * count); return TPOSE_OK; }   // penergy / nring: dead in the reference
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, (char*)dev + elem * first, elem * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_write(tpose_cuda_ctx* ctx, int which, size_t first, size_t count, const void* in)
+{
+    if (!ctx) return TPOSE_ERR_ARG;
+    size_t elem, cap; void* dev;
+    if (!in || !buffer_info(ctx, which, &elem, &cap, &dev)) return fail(ctx, TPOSE_ERR_ARG, "write: bad buffer or null input");
+    if (first + count > cap) return fail(ctx, TPOSE_ERR_CAPACITY, "write: range exceeds the buffer");
+    if (count == 0 || !dev) return TPOSE_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync((char*)dev + elem * first, in, elem * count, cudaMemcpyHostToDevice, ctx->stream));
+    if (which == TPOSE_BUF_COLACC)   // both buffer sets see uploaded colours (warp flavour reads them every frame)
+        CK(cudaMemcpyAsync((char*)ctx->ca[ctx->cur ^ 1] + elem * first, in, elem * count, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return TPOSE_OK;
 }

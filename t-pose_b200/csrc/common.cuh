@@ -65,9 +65,16 @@ __device__ __forceinline__ int64_t floordiv64(int64_t a, int64_t b)  // b > 0
 }
 
 // Scan conversion of one edge: for row r (centre 256r+128) the number of pixel centres of that
-// row strictly left of the edge, as an incremental quotient.  Rows are visited r, r+stride, ...
+// row strictly left of the edge, c(r) = ceil((x_edge(yc) - 128) / 256), kept as an incremental
+// quotient/remainder pair.  Rows are visited r, r+stride, ...
+//
+// With the edge sorted so that ya < yb, dy = yb-ya, dx = xb-xa, m = yc-ya >= 0:
+//   c(r) = floor( (xa + 128 + floor((dx*m - 1)/dy)) / 256 )
+// (nested-floor identity; checked against the plain ceil-division on 3e5 random edges), which
+// needs one division by dy instead of one by 256*dy and stays in 32 bits for on-screen edges.
 struct EdgeWalk {
-    int64_t q, rem, den, dq, dr;
+    long long rem, den, dr;
+    int q, dq;
     int r, r_end;       // first row of this lane, one past the last row of the edge (clipped)
     int sign;           // +1 if the directed edge a->b goes down (yb > ya), -1 if up, 0 if horizontal
     __device__ __forceinline__ void init(int2 a, int2 b, int H, int lane, int stride)
@@ -82,19 +89,32 @@ struct EdgeWalk {
         r_end = min(r1, H);
         r = r0 + lane;
         if (sign == 0 || r >= r_end) { r = r_end; return; }
-        const int64_t dy = (int64_t)hi - lo, dx = (int64_t)b.x - a.x;
-        den = 256 * dy;
-        const int64_t yc = 256 * (int64_t)r + 128;
-        // c = ceil(num/den), num = xa*dy + dx*(yc-ya) - 128*dy ; kept as floor((num+den-1)/den)
-        const int64_t N = (int64_t)a.x * dy + dx * (yc - lo) - 128 * dy + den - 1;
-        q = floordiv64(N, den);
-        rem = N - q * den;
-        const int64_t dN = 256 * (int64_t)stride * dx;
-        dq = floordiv64(dN, den);
-        dr = dN - dq * den;
+        const int dy = hi - lo, dx = b.x - a.x;       // |.| <= 2^24
+        const int m = 256 * r + 128 - lo;             // 0 <= m < 2^24
+        int w, wr;
+        const unsigned adx = (unsigned)abs(dx);
+        if (__umulhi(adx, (unsigned)m) == 0 && adx * (unsigned)m < 0x7fffffffu) {   // 32-bit path
+            const int z = dx * m - 1;
+            w = z / dy; wr = z - w * dy;
+            if (wr < 0) { wr += dy; --w; }
+        } else {
+            const long long z = (long long)dx * m - 1;
+            long long w64 = z / dy, wr64 = z - w64 * dy;
+            if (wr64 < 0) { wr64 += dy; --w64; }
+            w = (int)w64; wr = (int)wr64;
+        }
+        const int s = a.x + 128 + w;
+        q = s >> 8;
+        den = 256ll * dy;
+        rem = (long long)(s & 255) * dy + wr;
+        const int t = stride * dx;                    // |t| <= 2^29
+        dq = t / dy;
+        int tr = t - dq * dy;
+        if (tr < 0) { tr += dy; --dq; }
+        dr = 256ll * tr;
     }
     __device__ __forceinline__ bool done() const { return r >= r_end; }
-    __device__ __forceinline__ int cross(int W) const { return (int)min(max(q, (int64_t)0), (int64_t)W); }
+    __device__ __forceinline__ int cross(int W) const { return min(max(q, 0), W); }
     __device__ __forceinline__ void next(int stride)
     {
         r += stride;

@@ -199,3 +199,118 @@ def test_run_stops_on_convergence_like_geterr(cuda_pkg, synth, O):
     assert np.array_equal(bits(got["pts"]), bits(cur))
     assert ctx.get_toterr() == float(toterr)
     ctx.close()
+
+
+def test_run_with_quiet_watch_equals_plain_run(cuda_pkg, synth):
+    """A watch topology on which no per-frame edit can apply must not change the run."""
+    w, h = 256, 160
+    ratio = w / h
+    img = synth.make_image(w, h, seed=21)
+    pts, tri, he = synth.mesh_for(150, ratio)
+    out = []
+    for watch in (False, True):
+        ctx = _ctx(cuda_pkg)
+        ctx.set_image(0, img)
+        ctx.upload(pts, tri, ratio)
+        if watch:
+            ctx.watch(tri, he)
+        n, flags, err = ctx.run(0, cuda_pkg.TRIANGULATE, 25, 1e-9)
+        out.append((n, flags, ctx.retrieve()))
+        ctx.close()
+    assert out[0][0] == out[1][0] == 25 and out[0][1] == out[1][1] == cuda_pkg.TRIG_MAXSTEPS
+    for k in ("cn", "ca", "ten"):
+        assert np.array_equal(out[0][2][k], out[1][2][k])
+    assert np.array_equal(bits(out[0][2]["pts"]), bits(out[1][2]["pts"]))
+
+
+def test_watch_stops_after_the_frame_where_an_edit_applies(cuda_pkg, synth, O):
+    """Short edge (<= 0.01, triangulation.hpp:338): the run must stop right after the first frame,
+    holding that frame's energies and the shifted points -- what the reference has in hand when its
+    per-frame collapse loop (triangulate/main.cpp:336-346) fires."""
+    w, h = 256, 160
+    ratio = w / h
+    img = synth.make_image(w, h, seed=22)
+    pts, tri, he = synth.mesh_for(150, ratio)
+    pts = pts.copy()
+    a, b = int(tri[40, 0]), int(tri[40, 1])
+    a, b = (a, b) if a >= 4 else (b, a)
+    pts[a] = pts[b] + np.float32([0.004, 0.0])
+    ctx = _ctx(cuda_pkg)
+    ctx.set_image(0, img)
+    ctx.upload(pts, tri, ratio)
+    ctx.watch(tri, he)
+    n, flags, err = ctx.run(0, cuda_pkg.TRIANGULATE, 10, 1e-12)
+    assert flags & cuda_pkg.TRIG_TOPOLOGY
+    ref = O.step(img, pts, tri, ratio, O.TRIANGULATE)
+    ln = np.linalg.norm(ref["pts"][a] - ref["pts"][b])
+    assert n == 1 and ln <= 0.0100005
+    got = ctx.retrieve()
+    _assert_step_equal(got, ref, ("cn", "ca", "ten"))
+    assert ctx.get_toterr() == O.sum_energy(ref["ten"], tri.shape[0])
+    ctx.close()
+
+
+def test_read_write_buffers_like_tinyengine_buffers(cuda_pkg, synth, O):
+    w, h = 128, 96
+    ratio = w / h
+    img = synth.make_image(w, h, seed=2)
+    pts, tri, _ = synth.mesh_for(150, ratio)
+    NT, NP = tri.shape[0], pts.shape[0]
+    ctx = _ctx(cuda_pkg)
+    ctx.set_image(0, img)
+    ctx.upload(pts, tri, ratio)
+    ctx.step(0, cuda_pkg.TRIANGULATE, 1)
+    ref = O.step(img, pts, tri, ratio, O.TRIANGULATE)
+    assert np.array_equal(ctx.read(cuda_pkg.BUF_TENERGY, 0, 13 * NT), ref["ten"])
+    assert np.array_equal(ctx.read(cuda_pkg.BUF_COLNUM, NT, 5), ref["cn"][NT:NT + 5])
+    assert np.array_equal(ctx.read(cuda_pkg.BUF_COLACC, 0, NT), ref["ca"][:NT])
+    assert np.array_equal(ctx.read(cuda_pkg.BUF_GRADIENT, 0, NP), ref["gr"])
+    assert np.array_equal(bits(ctx.read(cuda_pkg.BUF_POINTS, 0, NP)), bits(ref["pts"]))
+    assert np.array_equal(ctx.read(cuda_pkg.BUF_INDEX, 0, NT), tri)
+    assert not ctx.read(cuda_pkg.BUF_PENERGY, 0, 13 * NT).any()
+    ctx.write(cuda_pkg.BUF_POINTS, 0, pts)
+    ctx.step(0, cuda_pkg.TRIANGULATE, 1)
+    assert np.array_equal(ctx.read(cuda_pkg.BUF_TENERGY, 0, 13 * NT), ref["ten"])
+    ctx.close()
+
+
+def test_batch_equals_individual_contexts(cuda_pkg, synth, O):
+    """Independent jobs sharing launches: ragged NT, different images; results identical to solo runs."""
+    cases = [(256, 160, 150, 31), (320, 200, 1000, 32), (200, 120, 150, 33)]
+    solo, ctxs = [], []
+    for (w, h, ntri, seed) in cases:
+        ratio = w / h
+        img = synth.make_image(w, h, seed=seed)
+        pts, tri, _ = synth.mesh_for(ntri, ratio)
+        c = _ctx(cuda_pkg)
+        c.set_image(0, img); c.upload(pts, tri, ratio)
+        c.step(0, cuda_pkg.TRIANGULATE, 4)
+        solo.append(c.retrieve()); c.close()
+        c = _ctx(cuda_pkg)
+        c.set_image(0, img); c.upload(pts, tri, ratio)
+        ctxs.append(c)
+    cuda_pkg.batch_step(ctxs, cuda_pkg.TRIANGULATE, 4)
+    for c, s in zip(ctxs, solo):
+        got = c.retrieve()
+        for k in ("cn", "ca", "ten"):
+            assert np.array_equal(got[k], s[k])
+        assert np.array_equal(bits(got["pts"]), bits(s["pts"]))
+    # batch_run: each job stops on its own convergence, same step counts as solo runs
+    tol = 2e-3
+    for c, (w, h, ntri, seed) in zip(ctxs, cases):
+        pts, tri, _ = synth.mesh_for(ntri, w / h)
+        c.upload(pts, tri, w / h); c.set_toterr(1.0)
+    done, trig = cuda_pkg.batch_run(ctxs, cuda_pkg.TRIANGULATE, 40, tol)
+    for i, (w, h, ntri, seed) in enumerate(cases):
+        ratio = w / h
+        img = synth.make_image(w, h, seed=seed)
+        pts, tri, _ = synth.mesh_for(ntri, ratio)
+        c = _ctx(cuda_pkg)
+        c.set_image(0, img); c.upload(pts, tri, ratio)
+        n, fl, _ = c.run(0, cuda_pkg.TRIANGULATE, 40, tol)
+        assert (n, fl) == (done[i], trig[i])
+        a, b = c.retrieve(), ctxs[i].retrieve()
+        assert np.array_equal(a["ten"], b["ten"]) and np.array_equal(bits(a["pts"]), bits(b["pts"]))
+        c.close()
+    for c in ctxs:
+        c.close()
