@@ -135,7 +135,7 @@ int tpose_cuda_step(tpose_cuda_ctx *ctx, int slot, int flavour, int nsteps);
  * `toterr` lives in the context (it is a global in the reference, starts at 1
  * and persists across levels); tpose_cuda_set_toterr overrides it.
  * steps_done / trigger_flags / last_err (|relerr| of the last frame) may be NULL. */
-int tpose_cuda_run(tpose_cuda_ctx *ctx, int slot, int flavour, int max_steps, float rel_tol,
+int tpose_cuda_run(tpose_cuda_ctx *ctx, int slot, int flavour, int max_steps, double rel_tol,
                    int *steps_done, uint32_t *trigger_flags, float *last_err);
 int tpose_cuda_set_toterr(tpose_cuda_ctx *ctx, float toterr);
 int tpose_cuda_get_toterr(tpose_cuda_ctx *ctx, float *toterr);
@@ -156,7 +156,7 @@ int tpose_cuda_watch(tpose_cuda_ctx *ctx, const int32_t *tri_xyzw, const int32_t
  * identical to running each context alone.  Work is issued on ctxs[0]'s stream. */
 int tpose_cuda_batch_step(tpose_cuda_ctx *const *ctxs, int n, const int *slots, int flavour, int nsteps);
 int tpose_cuda_batch_run(tpose_cuda_ctx *const *ctxs, int n, const int *slots, int flavour, int max_steps,
-                         float rel_tol, int *steps_done, uint32_t *trigger_flags);
+                         double rel_tol, int *steps_done, uint32_t *trigger_flags);
 
 /* ---- read back ---------------------------------------------------------- */
 

@@ -138,7 +138,7 @@ class Context:
 
     def run(self, slot, flavour, max_steps, rel_tol):
         n, f, e = C.c_int(), C.c_uint32(), C.c_float()
-        self._ck(lib().tpose_cuda_run(self._h, slot, flavour, max_steps, C.c_float(rel_tol),
+        self._ck(lib().tpose_cuda_run(self._h, slot, flavour, max_steps, C.c_double(rel_tol),
                                       C.byref(n), C.byref(f), C.byref(e)))
         return n.value, f.value, e.value
 
@@ -230,7 +230,7 @@ def batch_run(ctxs, flavour, max_steps, rel_tol, slots=None):
     sl = None if slots is None else (C.c_int * len(ctxs))(*slots)
     done = (C.c_int * len(ctxs))()
     trig = (C.c_uint32 * len(ctxs))()
-    rc = lib().tpose_cuda_batch_run(_handles(ctxs), len(ctxs), sl, flavour, max_steps, C.c_float(rel_tol), done, trig)
+    rc = lib().tpose_cuda_batch_run(_handles(ctxs), len(ctxs), sl, flavour, max_steps, C.c_double(rel_tol), done, trig)
     if rc != 0:
         raise TposeCudaError(f"batch_run -> {rc}: {lib().tpose_cuda_last_error(ctxs[0]._h).decode()}")
     return list(done), list(trig)

@@ -276,13 +276,13 @@ static int pick_group(const tpose_cuda_ctx* ctx, int NT, int H)
 }
 
 template <int G, int TPB>
-static void launch_eval(const EvalJob* jobs, int njobs, int max_nt, int set, unsigned flags, float tol, cudaStream_t st)
+static void launch_eval(const EvalJob* jobs, int njobs, int max_nt, int set, unsigned flags, double tol, cudaStream_t st)
 {
     const dim3 grid((max_nt + TPB - 1) / TPB, njobs);
     k_eval<G, TPB><<<grid, EvalCfg<G, TPB>::kThreads, 0, st>>>(jobs, set, flags, tol);
 }
 
-static void launch_eval_group(int group, const EvalJob* jobs, int njobs, int max_nt, int set, unsigned flags, float tol, cudaStream_t st)
+static void launch_eval_group(int group, const EvalJob* jobs, int njobs, int max_nt, int set, unsigned flags, double tol, cudaStream_t st)
 {
     switch (group) {
     case 1: launch_eval<1, 8>(jobs, njobs, max_nt, set, flags, tol, st); break;
@@ -326,7 +326,7 @@ static int sync_job(tpose_cuda_ctx* ctx, int slot, int flavour)
     return TPOSE_OK;
 }
 
-static int eval(tpose_cuda_ctx* ctx, int slot, int flavour, int set, unsigned flags, float tol = 0.0f)
+static int eval(tpose_cuda_ctx* ctx, int slot, int flavour, int set, unsigned flags, double tol = 0.0)
 {
     int rc = sync_job(ctx, slot, flavour);
     if (rc) return rc;
@@ -405,7 +405,7 @@ extern "C" int tpose_cuda_step(tpose_cuda_ctx* ctx, int slot, int flavour, int n
 // Launch j evaluates the points after j shifts into set (first+j)&1 and carries the checks of frame
 // j-1; launch max_steps is check-only.  See eval.cuh.
 static void issue_run(tpose_cuda_ctx* lead, const EvalJob* jobs, int njobs, int max_nt, int group, int first_set,
-                      int flavour, int max_steps, float rel_tol)
+                      int flavour, int max_steps, double rel_tol)
 {
     const unsigned fl = fused_flags(flavour) | EV_HONOUR_STOP;
     for (int j = 0; j <= max_steps; j++) {
@@ -417,7 +417,7 @@ static void issue_run(tpose_cuda_ctx* lead, const EvalJob* jobs, int njobs, int 
     }
 }
 
-extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int max_steps, float rel_tol,
+extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int max_steps, double rel_tol,
                               int* steps_done, uint32_t* trigger_flags, float* last_err)
 {
     int rc = check_ready(ctx, slot, flavour);
@@ -531,7 +531,7 @@ extern "C" int tpose_cuda_batch_step(tpose_cuda_ctx* const* ctxs, int n, const i
     int cur = ctx->cur;
     for (int s = 0; s < nsteps; s++) {
         cur ^= 1;
-        launch_eval_group(group, ctx->batch_jobs, n, max_nt, cur, fl, 0.0f, ctx->stream);
+        launch_eval_group(group, ctx->batch_jobs, n, max_nt, cur, fl, 0.0, ctx->stream);
         ctx->launches++;
     }
     CK(cudaGetLastError());
@@ -541,7 +541,7 @@ extern "C" int tpose_cuda_batch_step(tpose_cuda_ctx* const* ctxs, int n, const i
 }
 
 extern "C" int tpose_cuda_batch_run(tpose_cuda_ctx* const* ctxs, int n, const int* slots, int flavour, int max_steps,
-                                    float rel_tol, int* steps_done, uint32_t* trigger_flags)
+                                    double rel_tol, int* steps_done, uint32_t* trigger_flags)
 {
     int max_nt = 0, group = 1;
     int rc = batch_prepare(ctxs, n, slots, flavour, &max_nt, &group);

@@ -150,7 +150,7 @@ __device__ bool watch_triangle(const EvalJob& J, int t)
 
 // geterr (source/triangulation.hpp:653-674): float32 running sum of the base energies in index
 // order -- order matters, so it is one thread.
-__device__ void geterr_serial(const int* __restrict__ ten_base, int nt, float* state, float rel_tol)
+__device__ void geterr_serial(const int* __restrict__ ten_base, int nt, float* state, double rel_tol)
 {
     float newerr = 0.0f;
     int i = 0;
@@ -167,7 +167,8 @@ __device__ void geterr_serial(const int* __restrict__ ten_base, int nt, float* s
     state[0] = newerr;
     state[1] = fabsf(rel);
     state[2] = newerr;
-    state[3] = (fabsf(rel) < rel_tol) ? 1.0f : 0.0f;
+    // the reference compares the float against a double literal (`geterr(&tr) < 1E-4`)
+    state[3] = ((double)fabsf(rel) < rel_tol) ? 1.0f : 0.0f;
 }
 
 // G lanes cooperate on one edge variant; TPB triangles per block; one extra service warp.
@@ -180,7 +181,7 @@ struct EvalCfg {
 
 template <int G, int TPB>
 __global__ void __launch_bounds__(EvalCfg<G, TPB>::kThreads)
-k_eval(const EvalJob* __restrict__ jobs, int set, unsigned flags, float rel_tol)
+k_eval(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_tol)
 {
     using Cfg = EvalCfg<G, TPB>;
     constexpr int kItems = Cfg::kItems;

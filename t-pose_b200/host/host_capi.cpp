@@ -1,0 +1,180 @@
+// host_capi.cpp -- C entry points over the C++ host layer (include/tpose/*), so that the Python
+// test-suite and bench can drive the product's own tpose::triangulation / tpose::io /
+// tpose::schedule code.  Mirrors, name for name, the wrapper the tests put around the reference's
+// unmodified headers (oracle/ref_shim/ref_capi.cpp: ref_* there, tph_* here).
+#include <tpose/tpose>
+#include <tpose/triangulation>
+#include <tpose/io>
+#include <tpose/schedule>
+// #include <tpose/multiview>
+
+#include <sstream>
+
+using tpose::triangulation;
+
+namespace {
+std::ostringstream g_sink;
+struct Quiet {
+    std::streambuf* old;
+    Quiet() : old(std::cout.rdbuf(g_sink.rdbuf())) {}
+    ~Quiet() { std::cout.rdbuf(old); g_sink.str(""); }
+};
+}  // namespace
+
+extern "C" {
+
+void tph_set_ratio(float r) { tpose::RATIO = r; }
+float tph_get_ratio() { return tpose::RATIO; }
+
+void* tph_tri_new() { return new triangulation(); }
+void tph_tri_free(void* h) { delete (triangulation*)h; }
+void tph_tri_counts(void* h, int* nt, int* np) { auto* t = (triangulation*)h; *nt = t->NT; *np = t->NP; }
+void tph_tri_sizes(void* h, int* ntri, int* nhe, int* npts, int* nopts)
+{
+    auto* t = (triangulation*)h;
+    *ntri = (int)t->triangles.size(); *nhe = (int)t->halfedges.size();
+    *npts = (int)t->points.size(); *nopts = (int)t->originpoints.size();
+}
+void tph_tri_get(void* h, int* tri4, int* he, int* col4, float* pts, float* opts)
+{
+    auto* t = (triangulation*)h;
+    if (tri4) std::memcpy(tri4, t->triangles.data(), sizeof(glm::ivec4) * t->triangles.size());
+    if (he) std::memcpy(he, t->halfedges.data(), sizeof(int) * t->halfedges.size());
+    if (col4) std::memcpy(col4, t->colors.data(), sizeof(glm::ivec4) * t->triangles.size());
+    if (pts) std::memcpy(pts, t->points.data(), sizeof(glm::vec2) * t->points.size());
+    if (opts) std::memcpy(opts, t->originpoints.data(), sizeof(glm::vec2) * t->originpoints.size());
+}
+void tph_tri_set(void* h, int nt, const int* tri4, const int* he, const int* col4, int np, const float* pts, const float* opts)
+{
+    auto* t = (triangulation*)h;
+    t->NT = nt; t->NP = np;
+    t->triangles.resize(nt); t->halfedges.resize(3 * nt);
+    std::memcpy(t->triangles.data(), tri4, sizeof(glm::ivec4) * nt);
+    std::memcpy(t->halfedges.data(), he, sizeof(int) * 3 * nt);
+    if (col4) std::memcpy(t->colors.data(), col4, sizeof(glm::ivec4) * nt);
+    t->points.resize(np);
+    std::memcpy(t->points.data(), pts, sizeof(glm::vec2) * np);
+    if (opts) { t->originpoints.resize(np); std::memcpy(t->originpoints.data(), opts, sizeof(glm::vec2) * np); }
+}
+void tph_tri_set_points(void* h, const float* pts)
+{
+    auto* t = (triangulation*)h;
+    std::memcpy(t->points.data(), pts, sizeof(glm::vec2) * t->points.size());
+}
+void tph_tri_origin_from_points(void* h) { auto* t = (triangulation*)h; t->originpoints = t->points; }
+
+float tph_tri_angle(void* h, int ha) { return ((triangulation*)h)->angle(ha); }
+float tph_tri_hlength(void* h, int ha) { return ((triangulation*)h)->hlength(ha); }
+int tph_tri_boundary(void* h, int t) { return ((triangulation*)h)->boundary(t); }
+int tph_point_boundary(float x, float y) { return triangulation::boundary(glm::vec2(x, y)) ? 1 : 0; }
+int tph_tri_eraset(void* h, int t, int adjust) { return ((triangulation*)h)->eraset(t, adjust != 0); }
+int tph_tri_erasep(void* h, int p) { return ((triangulation*)h)->erasep(p); }
+int tph_tri_prune(void* h, int t) { return ((triangulation*)h)->prune(t); }
+int tph_tri_flip(void* h, int ha, float minangle) { return ((triangulation*)h)->flip(ha, minangle); }
+int tph_tri_flip_default(void* h, int ha) { return ((triangulation*)h)->flip(ha); }
+int tph_tri_collapse(void* h, int ha) { return ((triangulation*)h)->collapse(ha); }
+int tph_tri_split(void* h, int t) { return ((triangulation*)h)->split(t); }
+int tph_tri_optimize(void* h) { return ((triangulation*)h)->optimize(); }
+void tph_tri_warp(void* h, float* pts, int n)
+{
+    std::vector<glm::vec2> v(n);
+    std::memcpy(v.data(), pts, sizeof(glm::vec2) * n);
+    ((triangulation*)h)->warp(v);
+    std::memcpy(pts, v.data(), sizeof(glm::vec2) * n);
+}
+void tph_tri_reversewarp(void* h, float* pts, int n)
+{
+    std::vector<glm::vec2> v(n);
+    std::memcpy(v.data(), pts, sizeof(glm::vec2) * n);
+    ((triangulation*)h)->reversewarp(v);
+    std::memcpy(pts, v.data(), sizeof(glm::vec2) * n);
+}
+
+// tpose/utility
+void tph_barycentric(float px, float py, const int* t4, const float* verts, int nv, float* out3)
+{
+    std::vector<glm::vec2> v(nv);
+    std::memcpy(v.data(), verts, sizeof(glm::vec2) * nv);
+    glm::vec3 s = tpose::barycentric(glm::vec2(px, py), glm::ivec4(t4[0], t4[1], t4[2], t4[3]), v);
+    out3[0] = s.x; out3[1] = s.y; out3[2] = s.z;
+}
+int tph_intriangle(float px, float py, const int* t4, const float* verts, int nv)
+{
+    std::vector<glm::vec2> v(nv);
+    std::memcpy(v.data(), verts, sizeof(glm::vec2) * nv);
+    return tpose::intriangle(glm::vec2(px, py), glm::ivec4(t4[0], t4[1], t4[2], t4[3]), v) ? 1 : 0;
+}
+int tph_realroots(const double* a7, double* out6)
+{
+    std::vector<double> a(a7, a7 + 7);
+    std::vector<double> r = tpose::realroots(a);
+    for (size_t i = 0; i < r.size(); i++) out6[i] = r[i];
+    return (int)r.size();
+}
+double tph_horner(double x, const double* a, int n) { return tpose::horner(x, std::vector<double>(a, a + n)); }
+
+// tpose/io
+void tph_io_write(void* h, const char* path) { Quiet q; tpose::io::write((triangulation*)h, path); ((triangulation*)h)->out.flush(); }
+int tph_io_read(void* h, const char* path, int dowarp) { Quiet q; return tpose::io::read((triangulation*)h, path, dowarp != 0) ? 1 : 0; }
+void tph_io_close(void* h) { auto* t = (triangulation*)h; if (t->out.is_open()) t->out.close(); if (t->in.is_open()) t->in.close(); }
+int tph_io_readmatches(const char* path, float* a, float* b, int cap)
+{
+    Quiet q;
+    std::vector<glm::vec2> A, B;
+    if (!tpose::io::readmatches(path, A, B)) return -1;
+    const int n = (int)std::min<size_t>(A.size(), cap);
+    for (int i = 0; i < n; i++) { a[2 * i] = A[i].x; a[2 * i + 1] = A[i].y; b[2 * i] = B[i].x; b[2 * i + 1] = B[i].y; }
+    return (int)A.size();
+}
+
+// error reductions over host mirrors (no device needed: the mirrors are plain arrays)
+static void ensure_mirrors()
+{
+    if (tpose::terr) return;
+    tpose::terr = new int[triangulation::MAXT]();
+    tpose::perr = new int[triangulation::MAXT]();
+    tpose::cn = new int[triangulation::MAXT]();
+    tpose::col = new glm::ivec4[triangulation::MAXT]();
+}
+void tph_set_terr(const int* v, int n) { ensure_mirrors(); std::memcpy(tpose::terr, v, sizeof(int) * n); }
+void tph_set_cn(const int* v, int n) { ensure_mirrors(); std::memcpy(tpose::cn, v, sizeof(int) * n); }
+float tph_geterr(void* h) { return tpose::geterr((triangulation*)h); }
+float tph_gettoterr(void* h) { return tpose::gettoterr((triangulation*)h); }
+int tph_maxerrid(void* h) { return tpose::maxerrid((triangulation*)h); }
+float tph_get_toterr() { return tpose::toterr; }
+void tph_set_toterr(float v) { tpose::toterr = v; }
+float tph_get_relerr() { return tpose::relerr; }
+
+// ---- device-backed part --------------------------------------------------------------------------
+
+int tph_init(int device)
+{
+    if (tpose::context) return 0;
+    if (tpose::terr) { delete[] tpose::terr; delete[] tpose::perr; delete[] tpose::cn; delete[] tpose::col; tpose::terr = nullptr; }
+    tpose::init(device);
+    return 0;
+}
+void tph_quit() { if (tpose::context) tpose::quit(); }
+void tph_texture(int slot, const unsigned char* rgba, int w, int h, int rw, int rh) { tpose::texture(slot, rgba, w, h, rw, rh); }
+void tph_upload(void* h, int uploadcolor) { tpose::upload((triangulation*)h, uploadcolor != 0); }
+
+// report: frames, host_frames, runs, splits, exports, levels, finished
+void tph_triangulate(void* h, const int* exportlist, int nexport, const char* trifile, long max_frames, double tol, long* rep7)
+{
+    auto* t = (triangulation*)h;
+    Quiet q;
+    tpose::upload(t, false);
+    tpose::computecolors();
+    std::vector<int> ex(exportlist, exportlist + nexport);
+    const auto r = tpose::schedule::triangulate(*t, ex, trifile, max_frames, tol, false);
+    t->out.flush();
+    rep7[0] = r.frames; rep7[1] = r.host_frames; rep7[2] = r.runs; rep7[3] = r.splits; rep7[4] = r.exports; rep7[5] = r.levels; rep7[6] = r.finished;
+}
+void tph_warp(const char* triA, const char* triB, long max_frames, double tol, long* rep7)
+{
+    Quiet q;
+    const auto r = tpose::schedule::warp(triA, triB, max_frames, tol, false);
+    rep7[0] = r.frames; rep7[1] = r.host_frames; rep7[2] = r.runs; rep7[3] = r.splits; rep7[4] = r.exports; rep7[5] = r.levels; rep7[6] = r.finished;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+"""The program loops (include/tpose/schedule, driven by tpose_cuda_run with device-side checks)
+against the frame-by-frame CPU restatement of software/triangulate and software/warp
+(oracle/schedule_oracle.py: reference headers unmodified + per-fragment step oracle)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import hostlib as H
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.exists(H.REF_SO), reason="oracle/_ref not built")]
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_pkg):
+    L = H.ours()
+    L.f("init")(0)
+    yield L
+    L.f("quit")()
+
+
+def _triangulate_ours(L, img, ratio, exportlist, path, max_frames, raster=None):
+    h, w = img.shape[:2]
+    rw, rh = (w, h) if raster is None else raster
+    L.set_ratio(ratio)
+    L.f("set_toterr")(C.c_float(1.0))
+    L.f("texture")(0, img.ctypes.data_as(C.c_void_p), w, h, rw, rh)
+    tr = H.Tri(L)
+    ex = (C.c_int * len(exportlist))(*exportlist)
+    rep = (C.c_long * 7)()
+    L.f("triangulate")(tr.h, ex, len(exportlist), path.encode(), C.c_long(max_frames), C.c_double(1e-4), rep)
+    tr.io_close()
+    st = tr.get()
+    tr.close()
+    return dict(frames=rep[0], host_frames=rep[1], runs=rep[2], splits=rep[3], exports=rep[4], finished=bool(rep[6]), tr=st)
+
+
+@pytest.mark.parametrize("w,h,exportlist,seed", [(96, 64, [30, 20, 10], 4), (240, 160, [80, 40, 20], 5), (160, 160, [50, 25], 6)])
+def test_triangulate_schedule_equals_frame_by_frame_reference(dev, synth, tmp_path, w, h, exportlist, seed):
+    from oracle import schedule_oracle as S
+    img = synth.make_image(w, h, seed=seed)
+    ratio = float(np.float32(w) / np.float32(h))
+    fo, fr = str(tmp_path / "ours.tri"), str(tmp_path / "ref.tri")
+    ref = S.triangulate_loop(H.ref(), H.Tri, img, ratio, exportlist, fr, 30000)
+    got = _triangulate_ours(dev, img, ratio, exportlist, fo, 30000)
+    assert ref["finished"] and got["finished"]
+    assert got["frames"] == ref["frames"]
+    assert open(fo, "rb").read() == open(fr, "rb").read()
+    ok, where = H.same_state(got["tr"], ref["tr"])
+    assert ok, where
+    # the point of the device-side checks: the host body ran on a fraction of the frames
+    assert got["host_frames"] < got["frames"]
+
+
+def test_triangulate_schedule_frame_cap(dev, synth, tmp_path):
+    """max_frames stops both loops at the same state (mid-level, nothing exported yet)."""
+    from oracle import schedule_oracle as S
+    w, h = 200, 120
+    img = synth.make_image(w, h, seed=8)
+    ratio = float(np.float32(w) / np.float32(h))
+    for cap in (1, 37, 300):
+        fo, fr = str(tmp_path / f"o{cap}.tri"), str(tmp_path / f"r{cap}.tri")
+        ref = S.triangulate_loop(H.ref(), H.Tri, img, ratio, [1000], fr, cap)
+        got = _triangulate_ours(dev, img, ratio, [1000], fo, cap)
+        assert got["frames"] == ref["frames"] == cap
+        ok, where = H.same_state(got["tr"], ref["tr"])
+        assert ok, f"cap {cap}: {where}"
+
+
+def test_warp_schedule_equals_frame_by_frame_reference(dev, synth, tmp_path):
+    from oracle import schedule_oracle as S
+    w, h = 192, 128
+    a, b = synth.make_pair(w, h, seed=12)
+    ratio = float(np.float32(w) / np.float32(h))
+    ex = [60, 30, 12]
+    ta, tb = str(tmp_path / "a.tri"), str(tmp_path / "b.tri")
+    ga = _triangulate_ours(dev, a, ratio, ex, ta, 30000)
+    gb = _triangulate_ours(dev, b, ratio, ex, tb, 30000)
+    assert ga["finished"] and gb["finished"] and ga["exports"] == gb["exports"] == 3
+    # reference warp loop on copies of the stacks
+    ra, rb = str(tmp_path / "ra.tri"), str(tmp_path / "rb.tri")
+    for s, d in ((ta, ra), (tb, rb)):
+        open(d, "wb").write(open(s, "rb").read())
+    ref = S.warp_loop(H.ref(), H.Tri, a, b, ra, rb, 60000)
+    # ours
+    L = dev
+    L.f("set_toterr")(C.c_float(1.0))
+    L.f("texture")(0, a.ctypes.data_as(C.c_void_p), w, h, w, h)
+    L.f("texture")(1, b.ctypes.data_as(C.c_void_p), w, h, w, h)
+    rep = (C.c_long * 7)()
+    L.f("warp")(ta.encode(), tb.encode(), C.c_long(60000), C.c_double(1e-6), rep)
+    assert ref["finished"] and rep[6] == 1
+    assert rep[0] == ref["frames"] and rep[5] == ref["levels"] == 3
+    assert open(ta + ".warp", "rb").read() == open(ra + ".warp", "rb").read()
+    assert open(tb + ".warp", "rb").read() == open(rb + ".warp", "rb").read()
+    # the warp moved something
+    assert open(ta + ".warp", "rb").read() != open(ta, "rb").read()
