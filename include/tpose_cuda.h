@@ -189,6 +189,29 @@ int tpose_cuda_sync(tpose_cuda_ctx *ctx);
 /* Number of kernel launches issued by this context so far. */
 int64_t tpose_cuda_launch_count(const tpose_cuda_ctx *ctx);
 
+/* ---- multiview (source/multiview.hpp), batched; host pointers in and out -----------------
+ * These three need no context: pass the CUDA device ordinal.  Errors: tpose_cuda_mview_last_error. */
+
+/* mview::F_8Point (multiview.hpp:130-183) for nbatch independent match lists.  A_xy / B_xy: the
+ * lists concatenated (vec2 each); offsets[nbatch+1], offsets[0] = 0; F9_out: nbatch x 9 floats,
+ * row-major, scaled so that F(2,2) = 1.  An empty list yields the identity, like the reference. */
+int tpose_cuda_f8point(int device, const float *A_xy, const float *B_xy, const int *offsets, int nbatch,
+                       float *F9_out);
+/* mview::triangulate(F, K, A, B) (multiview.hpp:529-627): per match the Hartley-Sturm optimal
+ * correction (:415-527; skipped if optimal_correction == 0), then HDLT (:370-380) against
+ * PA = K[I|0], PB = K[R2|-t] from E = K^T F K (check = 3).  F9 / K9: one 3x3 per list.
+ * X4_out: vec4 per match, already divided by w.  A_corr / B_corr (may be NULL): corrected matches. */
+int tpose_cuda_triangulate(int device, const float *F9, const float *K9, const float *A_xy, const float *B_xy,
+                           const int *offsets, int nbatch, int optimal_correction, float *X4_out,
+                           float *A_corr, float *B_corr);
+/* mview::HDLT alone (multiview.hpp:370-380) for n matches with caller-supplied 3x4 projections
+ * (row-major float[12]).  X4_out is NOT divided by w; sign: largest component positive. */
+int tpose_cuda_hdlt(int device, const float *PA12, const float *PB12, const float *A_xy, const float *B_xy,
+                    int n, float *X4_out);
+const char *tpose_cuda_mview_last_error(void);
+/* device milliseconds of the kernel(s) of the most recent f8point / triangulate call */
+float tpose_cuda_mview_last_ms(void);
+
 /* Page-locked host memory for the buffers handed to set_image / upload / retrieve
  * (optional: pageable pointers work, pinned ones copy faster). */
 int tpose_cuda_host_alloc(size_t bytes, void **out);

@@ -11,8 +11,10 @@ pinned against cv2.findFundamentalMat(FM_8POINT) on the reference's own match li
 (tests/sfm_match_test/data.txt, 4e-5 element-wise) -- see tests/golden/make_golden.py.
 
 Conventions this file fixes (Eigen leaves them to its implementation; the CUDA path follows these):
-  * singular vectors: U and V of a 3x3 SVD are made proper rotations (det = +1) by choosing the sign
-    of their third column; only GetPose is sensitive to it (multiview.hpp:398-409 takes t = U.col(2));
+  * singular vectors: U and V of a 3x3 SVD are made proper rotations (det = +1, third columns =
+    cross products of the first two) and, of the two joint sign choices that leaves, the one where
+    the largest-magnitude component of V.col(2) is positive.  GetPose (multiview.hpp:398-409 takes
+    t = U.col(2); check = 3 picks [R2 | -t]) and the buggy root selection depend on it;
   * real roots of the sextic are taken in ascending order before the selection loop of
     multiview.hpp:492-501, which is restated literally INCLUDING its bug (cost evaluated at the loop
     index r, not at the root R[r]).
@@ -29,8 +31,9 @@ def _seqsum32(v):
 
 def camera():
     """multiview.hpp:35-52 (note: 1/fx on the diagonal, as coded)."""
-    px = f32(f32(488.421) / f32(960.0)); py = f32(f32(268.8) / f32(960.0))
-    fx = f32(f32(673.101) / f32(960.0)); fy = f32(f32(673.328) / f32(960.0))
+    # `float px = 488.421 / 960.0f;` -- a double division rounded to float once
+    px = f32(488.421 / 960.0); py = f32(268.8 / 960.0)
+    fx = f32(673.101 / 960.0); fy = f32(673.328 / 960.0)
     return np.array([[f32(1.0) / fx, 0, px], [0, f32(1.0) / fy, py], [0, 0, 1]], f32)
 
 
@@ -82,11 +85,14 @@ def f_8point(pa, pb):
 def svd3_proper(M):
     """3x3 SVD with det(U) = det(V) = +1 (sign of the third columns chosen)."""
     U, S, Vt = np.linalg.svd(np.asarray(M, np.float64))
-    V = Vt.T
-    # fix the gauge of the first two pairs: first non-negligible... keep LAPACK's pairing, only make
-    # the third columns the cross products of the first two
+    V = Vt.T.copy()
+    U = U.copy()
     U[:, 2] = np.cross(U[:, 0], U[:, 1])
     V[:, 2] = np.cross(V[:, 0], V[:, 1])
+    if V[np.argmax(np.abs(V[:, 2])), 2] < 0:
+        for Q in (U, V):
+            Q[:, 0] = -Q[:, 0]
+            Q[:, 2] = -Q[:, 2]
     return U, S, V
 
 

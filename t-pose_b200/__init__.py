@@ -43,6 +43,8 @@ EXPORTS = [
     "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
     "tpose_cuda_raster_ids", "tpose_cuda_last_elapsed_ms", "tpose_cuda_sync",
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
+    "tpose_cuda_f8point", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
+    "tpose_cuda_mview_last_ms",
     "tpose_cuda_watch", "tpose_cuda_read", "tpose_cuda_write", "tpose_cuda_batch_step", "tpose_cuda_batch_run",
 ]
 
@@ -234,6 +236,59 @@ def batch_run(ctxs, flavour, max_steps, rel_tol, slots=None):
     if rc != 0:
         raise TposeCudaError(f"batch_run -> {rc}: {lib().tpose_cuda_last_error(ctxs[0]._h).decode()}")
     return list(done), list(trig)
+
+
+def _mview_ck(rc, what):
+    if rc != 0:
+        lib().tpose_cuda_mview_last_error.restype = C.c_char_p
+        raise TposeCudaError(f"{what} -> {rc}: {lib().tpose_cuda_mview_last_error().decode()}")
+
+
+def _concat(lists):
+    offs = np.zeros(len(lists) + 1, np.int32)
+    offs[1:] = np.cumsum([len(x) for x in lists])
+    cat = np.concatenate([np.asarray(x, np.float32).reshape(-1, 2) for x in lists]) if offs[-1] else np.zeros((0, 2), np.float32)
+    return np.ascontiguousarray(cat, np.float32), offs
+
+
+def f8point(A_lists, B_lists, device=0):
+    """Batched mview::F_8Point: lists of (N_i, 2) float32 matches -> (nbatch, 3, 3) float32."""
+    A, offs = _concat(A_lists)
+    B, offs_b = _concat(B_lists)
+    assert np.array_equal(offs, offs_b), "matched sets have different size"
+    if A.shape[0] == 0:
+        A = np.zeros((1, 2), np.float32); B = np.zeros((1, 2), np.float32)
+    F = np.zeros((len(A_lists), 9), np.float32)
+    _mview_ck(lib().tpose_cuda_f8point(device, _ptr(A), _ptr(B), _ptr(offs), len(A_lists), _ptr(F)), "f8point")
+    return F.reshape(-1, 3, 3)
+
+
+def triangulate(F, K, A_lists, B_lists, correct=True, device=0):
+    """Batched mview::triangulate(F,K,A,B): returns (list of (N_i,4) points, corrected A, corrected B)."""
+    A, offs = _concat(A_lists)
+    B, _ = _concat(B_lists)
+    nb = len(A_lists)
+    F = np.ascontiguousarray(np.asarray(F, np.float32).reshape(nb, 9))
+    K = np.ascontiguousarray(np.broadcast_to(np.asarray(K, np.float32).reshape(-1, 9), (nb, 9)))
+    X = np.zeros((A.shape[0], 4), np.float32)
+    Ac, Bc = np.zeros_like(A), np.zeros_like(B)
+    _mview_ck(lib().tpose_cuda_triangulate(device, _ptr(F), _ptr(K), _ptr(A), _ptr(B), _ptr(offs), nb, int(correct),
+                                           _ptr(X), _ptr(Ac), _ptr(Bc)), "triangulate")
+    sp = lambda a: [a[offs[i]:offs[i + 1]] for i in range(nb)]
+    return sp(X), sp(Ac), sp(Bc)
+
+
+def hdlt(PA, PB, A, B, device=0):
+    PA = np.ascontiguousarray(PA, np.float32).reshape(12); PB = np.ascontiguousarray(PB, np.float32).reshape(12)
+    A = np.ascontiguousarray(A, np.float32).reshape(-1, 2); B = np.ascontiguousarray(B, np.float32).reshape(-1, 2)
+    X = np.zeros((A.shape[0], 4), np.float32)
+    _mview_ck(lib().tpose_cuda_hdlt(device, _ptr(PA), _ptr(PB), _ptr(A), _ptr(B), A.shape[0], _ptr(X)), "hdlt")
+    return X
+
+
+def mview_last_ms():
+    lib().tpose_cuda_mview_last_ms.restype = C.c_float
+    return float(lib().tpose_cuda_mview_last_ms())
 
 
 def pinned_empty(shape, dtype):

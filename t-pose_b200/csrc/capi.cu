@@ -2,12 +2,14 @@
 // There is no CPU path in this library: without a CUDA device every entry point fails.
 #include "../../include/tpose_cuda.h"
 #include "eval.cuh"
+#include "mview.cuh"
 #include "raster.cuh"
 #include "table.cuh"
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -715,5 +717,132 @@ extern "C" int tpose_cuda_flush_l2(tpose_cuda_ctx* ctx, size_t bytes)
     CK(cudaSetDevice(ctx->device));
     if (ctx->flush_cap < bytes) { cudaFree(ctx->flush); ctx->flush = nullptr; CK(cudaMalloc((void**)&ctx->flush, bytes)); ctx->flush_cap = bytes; }
     CK(cudaMemsetAsync(ctx->flush, 0x5a, bytes, ctx->stream));
+    return TPOSE_OK;
+}
+
+// ---- multiview (source/multiview.hpp) -----------------------------------------------------------
+
+namespace {
+std::string g_mview_error;
+float g_mview_ms = 0.0f;
+
+struct DevBuf {                       // RAII device allocation for one call
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T> T* as() { return (T*)p; }
+};
+
+int mview_fail(int code, const std::string& msg) { g_mview_error = msg; return code; }
+
+#define MCK(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) return mview_fail(TPOSE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+int mview_device(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        (void)cudaGetLastError();
+        return mview_fail(TPOSE_ERR_NODEVICE, "no usable CUDA device (this library has no CPU fallback)");
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return mview_fail(TPOSE_ERR_CUDA, "cudaSetDevice failed");
+    return TPOSE_OK;
+}
+
+bool offsets_ok(const int* offsets, int nbatch)
+{
+    if (!offsets || nbatch < 1 || offsets[0] != 0) return false;
+    for (int i = 0; i < nbatch; i++) if (offsets[i + 1] < offsets[i]) return false;
+    return true;
+}
+}  // namespace
+
+extern "C" const char* tpose_cuda_mview_last_error(void) { return g_mview_error.c_str(); }
+extern "C" float tpose_cuda_mview_last_ms(void) { return g_mview_ms; }
+
+extern "C" int tpose_cuda_f8point(int device, const float* A_xy, const float* B_xy, const int* offsets, int nbatch, float* F9_out)
+{
+    if (!A_xy || !B_xy || !F9_out || !offsets_ok(offsets, nbatch)) return mview_fail(TPOSE_ERR_ARG, "f8point: bad arguments");
+    int rc = mview_device(device);
+    if (rc) return rc;
+    const size_t n = (size_t)offsets[nbatch];
+    DevBuf dA, dB, dO, dF;
+    MCK(dA.alloc(n * sizeof(float2))); MCK(dB.alloc(n * sizeof(float2)));
+    MCK(dO.alloc((nbatch + 1) * sizeof(int))); MCK(dF.alloc((size_t)nbatch * 9 * sizeof(float)));
+    MCK(cudaMemcpy(dA.p, A_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dB.p, B_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dO.p, offsets, (nbatch + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    MCK(cudaEventCreate(&e0)); MCK(cudaEventCreate(&e1));
+    MCK(cudaEventRecord(e0, 0));
+    k_f8point<<<nbatch, kF8Threads>>>(dA.as<float2>(), dB.as<float2>(), dO.as<int>(), dF.as<float>());
+    MCK(cudaEventRecord(e1, 0));
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpy(F9_out, dF.p, (size_t)nbatch * 9 * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaEventElapsedTime(&g_mview_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_triangulate(int device, const float* F9, const float* K9, const float* A_xy, const float* B_xy,
+                                      const int* offsets, int nbatch, int optimal_correction, float* X4_out,
+                                      float* A_corr, float* B_corr)
+{
+    if (!F9 || !K9 || !A_xy || !B_xy || !X4_out || !offsets_ok(offsets, nbatch)) return mview_fail(TPOSE_ERR_ARG, "triangulate: bad arguments");
+    int rc = mview_device(device);
+    if (rc) return rc;
+    const size_t n = (size_t)offsets[nbatch];
+    int longest = 0;
+    for (int i = 0; i < nbatch; i++) longest = std::max(longest, offsets[i + 1] - offsets[i]);
+    DevBuf dA, dB, dO, dF, dK, dX, dAc, dBc;
+    MCK(dA.alloc(n * sizeof(float2))); MCK(dB.alloc(n * sizeof(float2)));
+    MCK(dO.alloc((nbatch + 1) * sizeof(int)));
+    MCK(dF.alloc((size_t)nbatch * 9 * sizeof(float))); MCK(dK.alloc((size_t)nbatch * 9 * sizeof(float)));
+    MCK(dX.alloc(n * sizeof(float4)));
+    if (A_corr) MCK(dAc.alloc(n * sizeof(float2)));
+    if (B_corr) MCK(dBc.alloc(n * sizeof(float2)));
+    MCK(cudaMemcpy(dA.p, A_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dB.p, B_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dO.p, offsets, (nbatch + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dF.p, F9, (size_t)nbatch * 9 * sizeof(float), cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dK.p, K9, (size_t)nbatch * 9 * sizeof(float), cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    MCK(cudaEventCreate(&e0)); MCK(cudaEventCreate(&e1));
+    MCK(cudaEventRecord(e0, 0));
+    if (longest > 0) {
+        const dim3 grid((longest + 127) / 128, nbatch);
+        k_triangulate<<<grid, 128>>>(dF.as<float>(), dK.as<float>(), dA.as<float2>(), dB.as<float2>(), dO.as<int>(),
+                                     optimal_correction, dX.as<float4>(), A_corr ? dAc.as<float2>() : nullptr,
+                                     B_corr ? dBc.as<float2>() : nullptr);
+    }
+    MCK(cudaEventRecord(e1, 0));
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpy(X4_out, dX.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (A_corr) MCK(cudaMemcpy(A_corr, dAc.p, n * sizeof(float2), cudaMemcpyDeviceToHost));
+    if (B_corr) MCK(cudaMemcpy(B_corr, dBc.p, n * sizeof(float2), cudaMemcpyDeviceToHost));
+    cudaEventElapsedTime(&g_mview_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_hdlt(int device, const float* PA12, const float* PB12, const float* A_xy, const float* B_xy,
+                               int n, float* X4_out)
+{
+    if (!PA12 || !PB12 || !A_xy || !B_xy || !X4_out || n < 1) return mview_fail(TPOSE_ERR_ARG, "hdlt: bad arguments");
+    int rc = mview_device(device);
+    if (rc) return rc;
+    DevBuf dA, dB, dPA, dPB, dX;
+    MCK(dA.alloc(n * sizeof(float2))); MCK(dB.alloc(n * sizeof(float2)));
+    MCK(dPA.alloc(12 * sizeof(float))); MCK(dPB.alloc(12 * sizeof(float))); MCK(dX.alloc(n * sizeof(float4)));
+    MCK(cudaMemcpy(dA.p, A_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dB.p, B_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dPA.p, PA12, 12 * sizeof(float), cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dPB.p, PB12, 12 * sizeof(float), cudaMemcpyHostToDevice));
+    k_hdlt<<<(n + 127) / 128, 128>>>(dPA.as<float>(), dPB.as<float>(), dA.as<float2>(), dB.as<float2>(), n, dX.as<float4>());
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpy(X4_out, dX.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
     return TPOSE_OK;
 }

@@ -1,0 +1,212 @@
+// mview.cuh -- the multiview half of the hot path (source/multiview.hpp of the reference), batched:
+//   k_f8point     one CTA per image pair: Hartley normalisation (multiview.hpp:62-87), the 9x9 normal
+//                 matrix A^T A of the N x 9 design matrix (:150-162) accumulated with FP64 tensor-core
+//                 MMAs (mma.sync.m8n8k4.f64 -> DMMA in SASS; the one genuinely dense contraction of
+//                 the path), its null vector by Jacobi, the rank-2 projection (:173-176) and the
+//                 de-normalisation (:178-179);
+//   k_triangulate one thread per match: optimal correction (:415-527), then HDLT (:370-380) with the
+//                 pose of E = K^T F K under check = 3 (:541-621).
+// A^T A in FP64 instead of a float32 SVD of A: float32 accumulation of A^T A misses the reference by
+// 1e-3, float64 by 1e-12 (hard part 5).  tcgen05 has no FP64 kind and a minimum
+// M of 64; the warp-level DMMA is the right size for a 9-wide problem.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/tpose/detail/smallmath.h"
+
+namespace tpose_dev {
+
+constexpr int kF8Threads = 256;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum of `v` (all threads get the result); s_red holds kF8Threads/32 doubles
+__device__ double block_sum(double v, double* s_red)
+{
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < kF8Threads / 32; w++) t += s_red[w];
+    return t;
+}
+
+struct Norm { float cx, cy, scale; };
+
+// multiview.hpp:62-87 -- centroid, mean distance, scale sqrt(2)/dist.  The reference sums in float32
+// in index order; here the sums are float64 tree reductions (the difference is far below the 1e-4
+// parity bound, and any (c, scale) is undone exactly by the returned H).
+__device__ Norm normalise_stats(const float2* __restrict__ p, int n, double* s_red)
+{
+    double sx = 0.0, sy = 0.0;
+    for (int i = threadIdx.x; i < n; i += kF8Threads) { sx += p[i].x; sy += p[i].y; }
+    const double tx = block_sum(sx, s_red), ty = block_sum(sy, s_red);
+    Norm r;
+    r.cx = (float)(tx / n); r.cy = (float)(ty / n);
+    double sd = 0.0;
+    for (int i = threadIdx.x; i < n; i += kF8Threads) {
+        const float dx = __fsub_rn(p[i].x, r.cx), dy = __fsub_rn(p[i].y, r.cy);
+        sd += (double)__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    }
+    const float dist = (float)(block_sum(sd, s_red) / n);
+    r.scale = (float)(sqrt(2.0) / (double)dist);
+    return r;
+}
+
+__device__ __forceinline__ float2 normalise_point(float2 p, const Norm& nm)
+{
+    return make_float2(__fmul_rn(__fsub_rn(p.x, nm.cx), nm.scale), __fmul_rn(__fsub_rn(p.y, nm.cy), nm.scale));
+}
+
+// column c (0..8) of the design-matrix row of one match, float32 products like the reference
+__device__ __forceinline__ float design_elem(float2 a, float2 b, int c)
+{
+    switch (c) {
+    case 0: return __fmul_rn(a.x, b.x);
+    case 1: return __fmul_rn(a.y, b.x);
+    case 2: return b.x;
+    case 3: return __fmul_rn(a.x, b.y);
+    case 4: return __fmul_rn(a.y, b.y);
+    case 5: return b.y;
+    case 6: return a.x;
+    case 7: return a.y;
+    default: return 1.0f;
+    }
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// offsets[nb+1]: match range of each pair inside A / B.  F9: nb x 9 floats, row-major.
+__global__ void __launch_bounds__(kF8Threads)
+k_f8point(const float2* __restrict__ A, const float2* __restrict__ B, const int* __restrict__ offsets, float* __restrict__ F9)
+{
+    __shared__ double s_red[kF8Threads / 32];
+    __shared__ double s_G[81];                 // A^T A
+    __shared__ double s_V[81];
+    const int pair = blockIdx.x;
+    const int o0 = offsets[pair], n = offsets[pair + 1] - o0;
+    float* out = F9 + 9 * pair;
+    if (n <= 0) {                              // multiview.hpp:139-142: empty set -> identity
+        if (threadIdx.x < 9) out[threadIdx.x] = (threadIdx.x % 4 == 0) ? 1.0f : 0.0f;
+        return;
+    }
+    const float2* pa = A + o0;
+    const float2* pb = B + o0;
+    const Norm na = normalise_stats(pa, n, s_red);
+    const Norm nb = normalise_stats(pb, n, s_red);
+    for (int i = threadIdx.x; i < 81; i += kF8Threads) s_G[i] = 0.0;
+    __syncthreads();
+
+    // 8x8 block of A^T A on the FP64 tensor cores: per MMA one warp contracts 4 matches.
+    // A-operand (8x4, row = lane/4, k = lane%4) and B-operand (4x8, k = lane%4, col = lane/4) are the
+    // same number: element `lane/4` of the design row of match `4*chunk + lane%4`.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = lane >> 2, kk = lane & 3;
+    double d0 = 0.0, d1 = 0.0, colsum = 0.0;
+    const int nchunks = (n + 3) >> 2;
+    for (int ch = warp; ch < nchunks; ch += kF8Threads / 32) {
+        const int i = 4 * ch + kk;
+        double e = 0.0;
+        if (i < n) e = (double)design_elem(normalise_point(pa[i], na), normalise_point(pb[i], nb), col);
+        colsum += e;
+        dmma_m8n8k4(d0, d1, e, e);
+    }
+    // accumulator fragment: row = lane/4, columns 2*(lane%4) and +1
+    atomicAdd(&s_G[col * 9 + 2 * kk], d0);
+    atomicAdd(&s_G[col * 9 + 2 * kk + 1], d1);
+    // ninth row / column: the design matrix's last column is all ones, so it is the column sums
+    colsum += __shfl_xor_sync(0xffffffffu, colsum, 1);
+    colsum += __shfl_xor_sync(0xffffffffu, colsum, 2);
+    if (kk == 0) { atomicAdd(&s_G[col * 9 + 8], colsum); atomicAdd(&s_G[8 * 9 + col], colsum); }
+    if (threadIdx.x == 0) s_G[80] = (double)n;
+    __syncthreads();
+
+    if (threadIdx.x != 0) return;
+    tpose::sm::jacobi_eigen<9>(s_G, s_V);
+    const int m = tpose::sm::argmin_diag<9>(s_G);
+    double F[9];
+    for (int i = 0; i < 9; i++) F[i] = (double)(float)s_V[i * 9 + m];      // VectorXf f -> Matrix3f F
+    tpose::sm::rank2_project(F);
+    // F = HB^T F HA; H = [[s,0,-cx s],[0,s,-cy s],[0,0,1]] with float32 entries (multiview.hpp:80-84)
+    const double HA[9] = {na.scale, 0, (double)__fmul_rn(-na.cx, na.scale), 0, na.scale, (double)__fmul_rn(-na.cy, na.scale), 0, 0, 1};
+    const double HB[9] = {nb.scale, 0, (double)__fmul_rn(-nb.cx, nb.scale), 0, nb.scale, (double)__fmul_rn(-nb.cy, nb.scale), 0, 0, 1};
+    double T[9], R[9];
+    tpose::sm::mat3_tmul(HB, F, T);
+    tpose::sm::mat3_mul(T, HA, R);
+    for (int i = 0; i < 9; i++) out[i] = (float)(R[i] / R[8]);
+}
+
+// One thread per match of one pair (blockIdx.y = pair).  F9 / K9: per pair, row-major float.
+// X4: homogeneous 3-D points divided by w (multiview.hpp:617-619); Ac / Bc (may be null) receive the
+// corrected matches.  do_correct = 0 skips the optimal correction (plain HDLT of the raw matches).
+__global__ void __launch_bounds__(128)
+k_triangulate(const float* __restrict__ F9, const float* __restrict__ K9, const float2* __restrict__ A,
+              const float2* __restrict__ B, const int* __restrict__ offsets, int do_correct,
+              float4* __restrict__ X4, float2* __restrict__ Ac, float2* __restrict__ Bc)
+{
+    __shared__ double s_F[9], s_KPA[12], s_KPB[12];
+    const int pair = blockIdx.y;
+    const int o0 = offsets[pair], n = offsets[pair + 1] - o0;
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    if (threadIdx.x == 0) {
+        double F[9], K[9], T[9], E[9], R1[9], R2[9], t[3];
+        for (int i = 0; i < 9; i++) { F[i] = F9[9 * pair + i]; K[i] = K9[9 * pair + i]; s_F[i] = F[i]; }
+        tpose::sm::mat3_tmul(K, F, T);                     // E = K^T F K (multiview.hpp:541)
+        tpose::sm::mat3_mul(T, K, E);
+        tpose::sm::get_pose(E, R1, R2, t);                 // check = 3: PB = [R2 | -t] (:584-588)
+        for (int r = 0; r < 3; r++) {
+            // K*PA = [K | 0]; K*PB = [K R2 | -K t]; both held as float32 like the reference's MatrixXf
+            for (int c = 0; c < 3; c++) {
+                s_KPA[r * 4 + c] = K[r * 3 + c];
+                s_KPB[r * 4 + c] = (double)(float)(K[r * 3] * R2[c] + K[r * 3 + 1] * R2[3 + c] + K[r * 3 + 2] * R2[6 + c]);
+            }
+            s_KPA[r * 4 + 3] = 0.0;
+            s_KPB[r * 4 + 3] = (double)(float)(-(K[r * 3] * t[0] + K[r * 3 + 1] * t[1] + K[r * 3 + 2] * t[2]));
+        }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a[2] = {A[o0 + i].x, A[o0 + i].y}, b[2] = {B[o0 + i].x, B[o0 + i].y};
+    if (do_correct) {
+        tpose::sm::correct_match(s_F, a, b);
+        a[0] = (double)(float)a[0]; a[1] = (double)(float)a[1];       // stored back into vec2 (:523-524)
+        b[0] = (double)(float)b[0]; b[1] = (double)(float)b[1];
+    }
+    if (Ac) Ac[o0 + i] = make_float2((float)a[0], (float)a[1]);
+    if (Bc) Bc[o0 + i] = make_float2((float)b[0], (float)b[1]);
+    double X[4];
+    tpose::sm::hdlt(s_KPA, s_KPB, a, b, X);
+    X4[o0 + i] = make_float4((float)(X[0] / X[3]), (float)(X[1] / X[3]), (float)(X[2] / X[3]), 1.0f);
+}
+
+// HDLT alone with caller-supplied 3x4 projections (multiview.hpp:370-380); X is NOT divided by w,
+// its sign is normalised so that the largest-magnitude component is positive.
+__global__ void __launch_bounds__(128)
+k_hdlt(const float* __restrict__ PA12, const float* __restrict__ PB12, const float2* __restrict__ A,
+       const float2* __restrict__ B, int n, float4* __restrict__ X4)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double PA[12], PB[12];
+    for (int k = 0; k < 12; k++) { PA[k] = PA12[k]; PB[k] = PB12[k]; }
+    const double a[2] = {A[i].x, A[i].y}, b[2] = {B[i].x, B[i].y};
+    double X[4];
+    tpose::sm::hdlt(PA, PB, a, b, X);
+    int big = 0;
+    for (int k = 1; k < 4; k++) if (fabs(X[k]) > fabs(X[big])) big = k;
+    const double s = X[big] < 0.0 ? -1.0 : 1.0;
+    X4[i] = make_float4((float)(s * X[0]), (float)(s * X[1]), (float)(s * X[2]), (float)(s * X[3]));
+}
+
+}  // namespace tpose_dev

@@ -6,7 +6,7 @@
 #include <tpose/triangulation>
 #include <tpose/io>
 #include <tpose/schedule>
-// #include <tpose/multiview>
+#include <tpose/multiview>
 
 #include <sstream>
 
@@ -176,5 +176,71 @@ void tph_warp(const char* triA, const char* triB, long max_frames, double tol, l
     const auto r = tpose::schedule::warp(triA, triB, max_frames, tol, false);
     rep7[0] = r.frames; rep7[1] = r.host_frames; rep7[2] = r.runs; rep7[3] = r.splits; rep7[4] = r.exports; rep7[5] = r.levels; rep7[6] = r.finished;
 }
+
+
+// ---- tpose/multiview ---------------------------------------------------------------------------------
+
+void tph_mview_device(int d) { tpose::mview::device = d; }
+void tph_camera(float* K9) { auto K = tpose::mview::Camera(); std::memcpy(K9, K.m, sizeof K.m); }
+void tph_normalize(float* pts, int n, float* H9)
+{
+    std::vector<glm::vec2> v(n);
+    std::memcpy(v.data(), pts, sizeof(glm::vec2) * n);
+    auto H = tpose::mview::normalize(v);
+    std::memcpy(pts, v.data(), sizeof(glm::vec2) * n);
+    std::memcpy(H9, H.m, sizeof H.m);
+}
+static std::vector<glm::vec2> vec2s(const float* p, int n)
+{
+    std::vector<glm::vec2> v(n);
+    if (n) std::memcpy(v.data(), p, sizeof(glm::vec2) * n);
+    return v;
+}
+void tph_f8point(const float* A, int na, const float* B, int nb, float* F9)
+{
+    Quiet q;
+    auto F = tpose::mview::F_8Point(vec2s(A, na), vec2s(B, nb));
+    std::memcpy(F9, F.m, sizeof F.m);
+}
+void tph_triangulate_points(const float* F9, const float* K9, const float* A, const float* B, int n, float* X4)
+{
+    tpose::mview::Matrix3f F, K;
+    std::memcpy(F.m, F9, sizeof F.m); std::memcpy(K.m, K9, sizeof K.m);
+    auto X = tpose::mview::triangulate(F, K, vec2s(A, n), vec2s(B, n));
+    std::memcpy(X4, X.data(), sizeof(glm::vec4) * n);
+}
+void tph_correct_match(const float* F9, float* a2, float* b2)
+{
+    tpose::mview::Matrix3f F; std::memcpy(F.m, F9, sizeof F.m);
+    glm::vec2 a(a2[0], a2[1]), b(b2[0], b2[1]);
+    tpose::mview::triangulate(F, a, b);
+    a2[0] = a.x; a2[1] = a.y; b2[0] = b.x; b2[1] = b.y;
+}
+void tph_hdlt(const float* PA12, const float* PB12, const float* a2, const float* b2, float* X4)
+{
+    tpose::mview::Matrix34f PA, PB; std::memcpy(PA.m, PA12, sizeof PA.m); std::memcpy(PB.m, PB12, sizeof PB.m);
+    tpose::mview::Vector3f xa, xb; xa(0) = a2[0]; xa(1) = a2[1]; xa(2) = 1; xb(0) = b2[0]; xb(1) = b2[1]; xb(2) = 1;
+    auto X = tpose::mview::HDLT(PA, PB, xa, xb);
+    std::memcpy(X4, X.m, sizeof X.m);
+}
+void tph_getpose(const float* E9, float* R1, float* R2, float* t3)
+{
+    tpose::mview::Matrix3f E; std::memcpy(E.m, E9, sizeof E.m);
+    auto P = tpose::mview::GetPose(E);
+    std::memcpy(R1, P.R1.m, 36); std::memcpy(R2, P.R2.m, 36); std::memcpy(t3, P.t.m, 12);
+}
+void tph_epole(const float* F9, int right, float* e2)
+{
+    tpose::mview::Matrix3f F; std::memcpy(F.m, F9, sizeof F.m);
+    auto e = tpose::mview::epole(F, right != 0); e2[0] = e.x; e2[1] = e.y;
+}
+// the shared host/device math, callable without a GPU (CPU tests pin it against the numpy oracle)
+int tph_sm_correct_match(const double* F9, double* a2, double* b2) { return tpose::sm::correct_match(F9, a2, b2); }
+void tph_sm_hdlt(const double* PA12, const double* PB12, const double* a2, const double* b2, double* X4) { tpose::sm::hdlt(PA12, PB12, a2, b2, X4); }
+void tph_sm_get_pose(const double* E9, double* R1, double* R2, double* t3) { tpose::sm::get_pose(E9, R1, R2, t3); }
+void tph_sm_svd3(const double* M9, double* U9, double* S3, double* V9) { tpose::sm::svd3_proper(M9, U9, S3, V9); }
+void tph_sm_rank2(double* F9) { tpose::sm::rank2_project(F9); }
+int tph_sm_realroots(const double* a7, double* out6) { return tpose::sm::realroots_sorted(a7, out6); }
+void tph_sm_jacobi9(double* A81, double* V81) { tpose::sm::jacobi_eigen<9>(A81, V81); }
 
 }  // extern "C"
