@@ -1,0 +1,51 @@
+// software/triangulate, headless: grows a minimum-energy triangulation of one image and appends the
+// levels of the export list to "<image>.tri" (software/triangulate/main.cpp of the reference; the
+// window, the key handlers and the mode-2 display are gone, the schedule is tpose/schedule).
+//
+//   triangulate -i image.ppm [-native] [-max N] [-frames F] [-device D]
+//     -native   rasterise at the image's own size instead of the reference's 1/1.5 window
+//     -max N    extend the export list beyond 1000 in steps of 500 up to N triangles
+//     -frames F stop after F optimisation steps
+#include <tpose/tpose>
+#include <tpose/triangulation>
+#include <tpose/io>
+#include <tpose/schedule>
+
+#include <chrono>
+
+#include "image_io.h"
+
+int main(int argc, char* args[])
+{
+    const std::string path = option(argc, args, "i");
+    if (path.empty()) { std::cout << "Please specify an input image with -i." << std::endl; return 0; }
+    Image img;
+    if (!load_image(path, img)) { std::cout << "Failed to load image." << std::endl; return 0; }
+
+    std::vector<int> exportlist = tpose::schedule::reference_exportlist();      // main.cpp:19-31
+    const int upto = atoi(option(argc, args, "max", "1000").c_str());
+    for (int n = 1500; n <= upto; n += 500) exportlist.insert(exportlist.begin(), n);
+    const long frames = atol(option(argc, args, "frames", "-1").c_str());
+
+    const bool native = has_flag(argc, args, "native");
+    const int rw = native ? img.w : (int)(img.w / 1.5), rh = native ? img.h : (int)(img.h / 1.5);   // main.cpp:53
+    tpose::RATIO = (float)img.w / (float)img.h;                                  // main.cpp:54
+
+    tpose::init(atoi(option(argc, args, "device", "0").c_str()));               // main.cpp:78
+    tpose::texture(TPOSE_IMAGE_A, img.rgba.data(), img.w, img.h, rw, rh);        // main.cpp:74
+
+    tpose::triangulation tr;                                                     // main.cpp:105-106
+    tpose::upload(&tr, false);
+    std::cout << "Number of Triangles: " << tr.NT << std::endl;
+    tpose::computecolors();                                                      // main.cpp:176
+
+    const auto t0 = std::chrono::steady_clock::now();
+    const auto rep = tpose::schedule::triangulate(tr, exportlist, path + ".tri", frames);
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::cout << "frames " << rep.frames << " (host body on " << rep.host_frames << "), splits " << rep.splits
+              << ", exports " << rep.exports << ", " << tr.NT << " triangles, " << sec << " s, "
+              << rep.frames / sec << " steps/s" << std::endl;
+
+    tpose::quit();
+    return 0;
+}

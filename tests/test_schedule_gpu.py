@@ -97,3 +97,34 @@ def test_warp_schedule_equals_frame_by_frame_reference(dev, synth, tmp_path):
     assert open(tb + ".warp", "rb").read() == open(rb + ".warp", "rb").read()
     # the warp moved something
     assert open(ta + ".warp", "rb").read() != open(ta, "rb").read()
+
+
+def test_ported_programs_write_the_same_files_as_the_library_calls(dev, synth, tmp_path):
+    """software/triangulate.cpp + software/warp.cpp (PPM in, .tri / .tri.warp out) end to end."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe_t = os.path.join(root, "t-pose_b200", "bin", "triangulate")
+    exe_w = os.path.join(root, "t-pose_b200", "bin", "warp")
+    if not (os.path.exists(exe_t) and os.path.exists(exe_w)):
+        pytest.fail("t-pose_b200/bin/* not built (run __graft_entry__.build())")
+    w, h = 192, 128
+    a, b = synth.make_pair(w, h, seed=3)
+    paths = []
+    for name, img in (("a", a), ("b", b)):
+        p = str(tmp_path / f"{name}.ppm")
+        with open(p, "wb") as f:
+            f.write(b"P6\n%d %d\n255\n" % (w, h)); f.write(img[..., :3].tobytes())
+        paths.append(p)
+        out = subprocess.run([exe_t, "-i", p, "-native", "-frames", "3000"], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and "steps/s" in out.stdout, out.stdout + out.stderr
+    # same job through the library entry point the other tests validate against the oracle
+    ratio = float(np.float32(w) / np.float32(h))
+    ex = [1000, 900, 800, 700, 600, 500, 400, 300, 200, 100, 50]
+    lib_a = str(tmp_path / "lib_a.tri")
+    _triangulate_ours(dev, a, ratio, ex, lib_a, 3000)
+    assert open(paths[0] + ".tri", "rb").read() == open(lib_a, "rb").read()
+    assert os.path.getsize(lib_a) > 0
+    out = subprocess.run([exe_w, "-ia", paths[0], "-ib", paths[1], "-ta", paths[0] + ".tri", "-tb", paths[1] + ".tri", "-native"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "levels" in out.stdout, out.stdout + out.stderr
+    assert os.path.getsize(paths[0] + ".tri.warp") == os.path.getsize(paths[0] + ".tri")
