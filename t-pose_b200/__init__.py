@@ -41,7 +41,7 @@ EXPORTS = [
     "tpose_cuda_upload_points", "tpose_cuda_colors", "tpose_cuda_energy", "tpose_cuda_shift",
     "tpose_cuda_step", "tpose_cuda_run", "tpose_cuda_set_toterr", "tpose_cuda_get_toterr",
     "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
-    "tpose_cuda_raster_ids", "tpose_cuda_last_elapsed_ms", "tpose_cuda_sync",
+    "tpose_cuda_raster_ids", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_sync",
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
     "tpose_cuda_f8point", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
     "tpose_cuda_mview_last_ms",
@@ -182,6 +182,10 @@ class Context:
         self._ck(lib().tpose_cuda_retrieve(self._h, _ptr(a_ten), _ptr(a_cn), _ptr(a_ca), _ptr(a_pts)))
         return dict(ten=a_ten, cn=a_cn, ca=a_ca, pts=a_pts)
 
+    def retrieve_into(self, ten=None, cn=None, ca=None, pts=None):
+        """Same read-back into caller-owned arrays (pinned ones copy without staging)."""
+        self._ck(lib().tpose_cuda_retrieve(self._h, _ptr(ten), _ptr(cn), _ptr(ca), _ptr(pts)))
+
     def retrieve_base(self):
         ten = np.empty(self.NT, np.int32)
         cn = np.empty(self.NT, np.int32)
@@ -204,6 +208,12 @@ class Context:
         ms = C.c_float()
         self._ck(lib().tpose_cuda_last_elapsed_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def last_kernel_ms(self):
+        """(k_edges ms, k_corners ms) of the most recent step(.., 1)."""
+        a, b = C.c_float(), C.c_float()
+        self._ck(lib().tpose_cuda_last_kernel_ms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def sync(self):
         self._ck(lib().tpose_cuda_sync(self._h))

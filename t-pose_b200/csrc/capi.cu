@@ -16,6 +16,13 @@
 
 using namespace tpose_dev;
 
+// Launch geometry of one evaluation.  Grid sizes are quantised (power of two, at most one full
+// wave) and the kernels stride, so a captured sequence stays valid while the mesh grows.
+struct EvalShape { int group, grid_e, grid_t; bool narrow; };
+// a sequence of evaluations (see issue_sequence) and its instantiated graph
+struct SeqKey { const EvalJob* jobs; int njobs; EvalShape shape; int kind, len, first_set; unsigned flags; double tol; };
+struct SeqGraph { SeqKey key; cudaGraphExec_t exec; uint64_t stamp; };
+
 struct ImageSlot {
     uchar4* rgba = nullptr;    // raster-resolution image on the device
     uint4* table = nullptr;    // row-prefix moments, (W+1) entries per row
@@ -33,13 +40,24 @@ struct tpose_cuda_ctx {
     bool have_mesh = false;
     ImageSlot img[2];
     uchar4* staging = nullptr; size_t staging_cap = 0;   // source-resolution upload buffer
+    // pinned ring for small uploads (points, triangles, colours): the caller's buffer is copied
+    // here and the H2D copy is asynchronous, so an upload does not stall the stream
+    static constexpr int kStageSlots = 4;
+    unsigned char* h_stage[kStageSlots] = {}; size_t h_stage_cap = 0; cudaEvent_t h_stage_ev[kStageSlots] = {}; int h_stage_next = 0;
     float2* pts = nullptr;
     int4* tri = nullptr;
     int* cn[2] = {nullptr, nullptr}; int4* ca[2] = {nullptr, nullptr}; int* ten[2] = {nullptr, nullptr};
     int cur = 0;                      // buffer set holding the last committed evaluation
-    int2* gr = nullptr; int2* gr_acc = nullptr;
+    int2* gr = nullptr;
+    // unique-edge view of the uploaded triangles (rebuilt on the host whenever they change)
+    std::vector<int32_t> tri_host;    // mirror of the index buffer, 4 ints per triangle
+    int2* edges = nullptr; int4* tri_edges = nullptr; int* corner_off = nullptr; int* corners = nullptr;
+    EdgeRec* rec = nullptr;
+    int NE = 0, edges_np = 0;
+    bool edges_dirty = true;
+    std::vector<uint64_t> scratch_keys; std::vector<int32_t> scratch_i32;
     int4* wtri = nullptr; int* whe = nullptr; bool watching = false;
-    unsigned* ticket = nullptr;       // [0] ticket [1] topology trigger accumulator
+    unsigned* ticket = nullptr;       // [1] topology trigger accumulator ([0] spare)
     float* err_state = nullptr;       // [0] toterr [1] |relerr| [2] newerr [3] converged flag
     int* run_state = nullptr;         // RS_STOP, RS_STEPS, RS_TRIG
     EvalJob* job_dev = nullptr;       // this context's job record (single launches)
@@ -48,10 +66,12 @@ struct tpose_cuda_ctx {
     EvalJob* batch_jobs = nullptr; int batch_cap = 0;   // job array when this context leads a batch
     int* ids = nullptr; size_t ids_cap = 0;
     unsigned char* flush = nullptr; size_t flush_cap = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;   // ev_mid: between k_edges and k_corners of a single step
     float last_ms = 0.0f;
     int64_t launches = 0;
     int group = 0;                    // lanes per edge (0 = pick from NT and H)
+    std::vector<SeqGraph> graphs; uint64_t graph_clock = 0; bool use_graphs = true;
+    bool mid_valid = false;
     std::string err;
 };
 
@@ -74,9 +94,28 @@ static int fail(tpose_cuda_ctx* ctx, int code, const char* msg)
     return code;
 }
 
+// Host -> device copy of a caller-owned buffer that the caller may reuse as soon as we return:
+// through the pinned ring when it fits (asynchronous), otherwise synchronous.
+static int upload_bytes(tpose_cuda_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (bytes == 0) return TPOSE_OK;
+    if (bytes <= ctx->h_stage_cap) {
+        const int slot = ctx->h_stage_next;
+        ctx->h_stage_next = (slot + 1) % tpose_cuda_ctx::kStageSlots;
+        CK(cudaEventSynchronize(ctx->h_stage_ev[slot]));          // the copy that last used this slot is done
+        memcpy(ctx->h_stage[slot], src, bytes);
+        CK(cudaMemcpyAsync(dst, ctx->h_stage[slot], bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->h_stage_ev[slot], ctx->stream));
+        return TPOSE_OK;
+    }
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TPOSE_OK;
+}
+
 extern "C" const char* tpose_cuda_version(void)
 {
-    return "tpose-cuda 0.1 (sm_100a; edge-integral evaluator over row-prefix moment tables)";
+    return "tpose-cuda 0.2 (sm_100a; shared-edge integrals over row-prefix moment tables)";
 }
 
 extern "C" const char* tpose_cuda_last_error(const tpose_cuda_ctx* ctx)
@@ -86,8 +125,8 @@ extern "C" const char* tpose_cuda_last_error(const tpose_cuda_ctx* ctx)
 
 extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, void* stream, tpose_cuda_ctx** out)
 {
-    if (!out || max_triangles <= 0 || max_points < 3 || 13ll * max_triangles > TPOSE_REF_MAXT) {
-        g_create_error = "tpose_cuda_create: bad arguments (need 13*max_triangles <= 2<<18)";
+    if (!out || max_triangles <= 0 || max_points < 3 || max_points > (1 << 21) || 13ll * max_triangles > TPOSE_REF_MAXT) {
+        g_create_error = "tpose_cuda_create: bad arguments (need 13*max_triangles <= 2<<18, max_points <= 2<<20)";
         return TPOSE_ERR_ARG;
     }
     int ndev = 0;
@@ -122,7 +161,11 @@ extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, 
         ALLOC(ctx->ten[s], sizeof(int) * nv);
     }
     ALLOC(ctx->gr, sizeof(int2) * max_points);
-    ALLOC(ctx->gr_acc, sizeof(int2) * max_points);
+    ALLOC(ctx->edges, sizeof(int2) * 3 * (size_t)max_triangles);
+    ALLOC(ctx->tri_edges, sizeof(int4) * max_triangles);
+    ALLOC(ctx->corner_off, sizeof(int) * ((size_t)max_points + 1));
+    ALLOC(ctx->corners, sizeof(int) * 3 * (size_t)max_triangles);
+    ALLOC(ctx->rec, sizeof(EdgeRec) * kEdgeMoves * 3 * (size_t)max_triangles);
     ALLOC(ctx->wtri, sizeof(int4) * max_triangles);
     ALLOC(ctx->whe, sizeof(int) * 3 * max_triangles);
     ALLOC(ctx->ticket, sizeof(unsigned) * 2);
@@ -136,16 +179,26 @@ extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, 
         cudaMemsetAsync(ctx->ten[s], 0, sizeof(int) * nv, ctx->stream);
     }
     cudaMemsetAsync(ctx->gr, 0, sizeof(int2) * max_points, ctx->stream);
-    cudaMemsetAsync(ctx->gr_acc, 0, sizeof(int2) * max_points, ctx->stream);
     cudaMemsetAsync(ctx->ticket, 0, sizeof(unsigned) * 2, ctx->stream);
     cudaMemsetAsync(ctx->run_state, 0, sizeof(int) * 4, ctx->stream);
     const float st[4] = {1.0f, 0.0f, 0.0f, 0.0f};   // toterr starts at 1 (triangulation.hpp:648)
     cudaMemcpyAsync(ctx->err_state, st, sizeof st, cudaMemcpyHostToDevice, ctx->stream);
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaEventCreate(&ctx->ev_mid);
+    {
+        const size_t cap = std::max(sizeof(int4) * (size_t)max_triangles, sizeof(float2) * (size_t)max_points);
+        bool ok = cap <= (4u << 20);
+        for (int i = 0; ok && i < tpose_cuda_ctx::kStageSlots; i++)
+            ok = cudaHostAlloc((void**)&ctx->h_stage[i], cap, cudaHostAllocDefault) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ctx->h_stage_ev[i], cudaEventDisableTiming) == cudaSuccess;
+        if (ok) ctx->h_stage_cap = cap; else (void)cudaGetLastError();
+    }
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("init", e);
     const char* g = getenv("TPOSE_CUDA_GROUP");
     if (g) ctx->group = atoi(g);
+    const char* ng = getenv("TPOSE_CUDA_NO_GRAPH");
+    if (ng && atoi(ng)) ctx->use_graphs = false;
     *out = ctx;
     return TPOSE_OK;
 }
@@ -155,14 +208,21 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
     if (!ctx) return TPOSE_ERR_ARG;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     for (auto& s : ctx->img) { cudaFree(s.rgba); cudaFree(s.table); }
     for (int s = 0; s < 2; s++) { cudaFree(ctx->cn[s]); cudaFree(ctx->ca[s]); cudaFree(ctx->ten[s]); }
     cudaFree(ctx->staging); cudaFree(ctx->pts); cudaFree(ctx->tri);
-    cudaFree(ctx->gr); cudaFree(ctx->gr_acc); cudaFree(ctx->wtri); cudaFree(ctx->whe); cudaFree(ctx->ticket);
+    cudaFree(ctx->edges); cudaFree(ctx->tri_edges); cudaFree(ctx->corner_off); cudaFree(ctx->corners); cudaFree(ctx->rec);
+    cudaFree(ctx->gr); cudaFree(ctx->wtri); cudaFree(ctx->whe); cudaFree(ctx->ticket);
     cudaFree(ctx->err_state); cudaFree(ctx->run_state); cudaFree(ctx->ids); cudaFree(ctx->flush);
     cudaFree(ctx->job_dev); cudaFree(ctx->batch_jobs);
+    for (int i = 0; i < tpose_cuda_ctx::kStageSlots; i++) {
+        if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
+        if (ctx->h_stage_ev[i]) cudaEventDestroy(ctx->h_stage_ev[i]);
+    }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TPOSE_OK;
@@ -217,7 +277,10 @@ static int set_image_common(tpose_cuda_ctx* ctx, int slot, const uint8_t* src, b
 
 extern "C" int tpose_cuda_set_image(tpose_cuda_ctx* ctx, int slot, const uint8_t* rgba_host, int w, int h, int rw, int rh)
 {
-    return set_image_common(ctx, slot, rgba_host, true, w, h, rw, rh);
+    int rc = set_image_common(ctx, slot, rgba_host, true, w, h, rw, rh);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));   // the caller may reuse (or free) its pixels
+    return TPOSE_OK;
 }
 
 extern "C" int tpose_cuda_set_image_device(tpose_cuda_ctx* ctx, int slot, const uint8_t* rgba_dev, int w, int h, int rw, int rh)
@@ -240,16 +303,22 @@ extern "C" int tpose_cuda_upload(tpose_cuda_ctx* ctx, const float* pts_xy, int n
             if (v < 0 || v >= np) return fail(ctx, TPOSE_ERR_ARG, "upload: triangle references a vertex outside [0,NP)");
         }
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(ctx->pts, pts_xy, sizeof(float2) * np, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->tri, tri_xyzw, sizeof(int4) * nt, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = upload_bytes(ctx, ctx->pts, pts_xy, sizeof(float2) * np);
+    if (rc) return rc;
+    if ((rc = upload_bytes(ctx, ctx->tri, tri_xyzw, sizeof(int4) * nt)) != 0) return rc;
+    if (nt != ctx->NT || np != ctx->edges_np || ctx->tri_host.size() != (size_t)4 * nt ||
+        memcmp(ctx->tri_host.data(), tri_xyzw, sizeof(int32_t) * 4 * nt) != 0) {
+        ctx->tri_host.assign(tri_xyzw, tri_xyzw + (size_t)4 * nt);
+        ctx->edges_dirty = true;
+    }
     if (colors_rgba) {   // triangulation.hpp:633-641: every variant row gets the triangle's colour
+        if ((rc = upload_bytes(ctx, ctx->ca[0], colors_rgba, sizeof(int4) * nt)) != 0) return rc;
         for (int s = 0; s < 2; s++)
-            for (int k = 0; k < kVariants; k++)
-                CK(cudaMemcpyAsync(ctx->ca[s] + (size_t)k * nt, colors_rgba, sizeof(int4) * nt, cudaMemcpyHostToDevice, ctx->stream));
+            for (int k = (s == 0 ? 1 : 0); k < kVariants; k++)
+                CK(cudaMemcpyAsync(ctx->ca[s] + (size_t)k * nt, ctx->ca[0], sizeof(int4) * nt, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     if (nt != ctx->NT) ctx->watching = false;   // a watch topology is only valid for the same NT
     ctx->NT = nt; ctx->NP = np; ctx->ratio = ratio; ctx->have_mesh = true;
-    CK(cudaStreamSynchronize(ctx->stream));   // caller may reuse its host buffers
     return TPOSE_OK;
 }
 
@@ -259,41 +328,217 @@ extern "C" int tpose_cuda_upload_points(tpose_cuda_ctx* ctx, const float* pts_xy
     if (!ctx->have_mesh) return fail(ctx, TPOSE_ERR_STATE, "upload_points: no mesh uploaded");
     if (!pts_xy || np != ctx->NP) return fail(ctx, TPOSE_ERR_ARG, "upload_points: NP differs from the uploaded mesh");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(ctx->pts, pts_xy, sizeof(float2) * np, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return TPOSE_OK;
+    return upload_bytes(ctx, ctx->pts, pts_xy, sizeof(float2) * np);
 }
 
 // ---- evaluation -----------------------------------------------------------------------------
 
-static int pick_group(const tpose_cuda_ctx* ctx, int NT, int H)
+// Unique-edge view of the uploaded triangles: side j of triangle t runs from corner j to corner
+// j+1; the two sides of an interior edge share one entry of `edges` (stored first < second end
+// point), so k_edges integrates it once.  Also the triangle corners that sit on every vertex
+// (k_corners evaluates the moved variants grouped by the vertex they move).
+static int rebuild_edges(tpose_cuda_ctx* ctx)
 {
-    if (ctx->group == 1 || ctx->group == 2 || ctx->group == 4 || ctx->group == 8 || ctx->group == 16 || ctx->group == 32)
-        return ctx->group;
-    // mean vertical extent of an edge is about H*sqrt(2/NT)*0.6; aim at <= ~8 rows per lane
-    const float rows = 0.6f * (float)H * sqrtf(2.0f / (float)NT);
+    if (!ctx->edges_dirty) return TPOSE_OK;
+    const int nt = ctx->NT, np = ctx->NP;
+    if (ctx->tri_host.size() < (size_t)4 * nt) return fail(ctx, TPOSE_ERR_STATE, "index buffer mirror is incomplete");
+    const int32_t* tri = ctx->tri_host.data();
+    for (int t = 0; t < nt; t++)
+        for (int j = 0; j < 3; j++)
+            if (tri[4 * t + j] < 0 || tri[4 * t + j] >= np)
+                return fail(ctx, TPOSE_ERR_ARG, "index buffer references a vertex outside [0,NP)");
+    std::vector<uint64_t>& keys = ctx->scratch_keys;
+    keys.resize((size_t)3 * nt);
+    for (int t = 0; t < nt; t++)
+        for (int j = 0; j < 3; j++) {
+            const uint32_t x = (uint32_t)tri[4 * t + j], y = (uint32_t)tri[4 * t + (j + 1) % 3];
+            const uint32_t lo = x < y ? x : y, hi = x < y ? y : x;
+            // (lo, hi) in the top 42 bits (indices < 2^21), the side slot below
+            keys[(size_t)3 * t + j] = ((uint64_t)lo << 43) | ((uint64_t)hi << 22) | (uint64_t)(3 * t + j);
+        }
+    std::sort(keys.begin(), keys.end());
+    std::vector<int32_t>& buf = ctx->scratch_i32;
+    // layout of buf: edges (2 per edge, 6*nt reserved) | tri_edges (4*nt) | corner_off (np+1) | corners (3*nt)
+    const size_t o_edges = 0, o_te = (size_t)6 * nt, o_off = o_te + (size_t)4 * nt, o_cor = o_off + np + 1;
+    buf.assign(o_cor + (size_t)3 * nt, 0);
+    int ne = 0;
+    uint64_t prev = ~0ull;
+    for (size_t i = 0; i < keys.size(); i++) {
+        const uint64_t pair = keys[i] >> 22;
+        const int slot = (int)(keys[i] & 0x3FFFFFu), t = slot / 3, j = slot - 3 * t;
+        const int lo = (int)(pair >> 21), hi = (int)(pair & 0x1FFFFFu);
+        if (pair != prev) { buf[o_edges + 2 * ne] = lo; buf[o_edges + 2 * ne + 1] = hi; ne++; prev = pair; }
+        const bool rev = tri[4 * t + j] > tri[4 * t + (j + 1) % 3];
+        buf[o_te + 4 * t + j] = (ne - 1) | (rev ? (int32_t)0x80000000u : 0);
+    }
+    // corners grouped by vertex (counting sort): gradient.cs sums a vertex's contributions, the
+    // order inside a group is irrelevant (wrapping integer adds)
+    for (int t = 0; t < nt; t++)
+        for (int j = 0; j < 3; j++) buf[o_off + tri[4 * t + j] + 1]++;
+    for (int v = 0; v < np; v++) buf[o_off + v + 1] += buf[o_off + v];
+    {
+        std::vector<int32_t> fill(buf.begin() + (long)o_off, buf.begin() + (long)o_off + np);
+        for (int t = 0; t < nt; t++)
+            for (int j = 0; j < 3; j++) buf[o_cor + fill[tri[4 * t + j]]++] = (t << 2) | j;
+    }
+    CK(cudaMemcpyAsync(ctx->edges, &buf[o_edges], sizeof(int2) * ne, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->tri_edges, &buf[o_te], sizeof(int4) * nt, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->corner_off, &buf[o_off], sizeof(int) * (np + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->corners, &buf[o_cor], sizeof(int) * 3 * nt, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // scratch is reused
+    ctx->NE = ne; ctx->edges_np = np;
+    ctx->edges_dirty = false;
+    return TPOSE_OK;
+}
+
+static bool valid_group(int g) { return g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32; }
+
+// lanes per (edge, move) item: the mean vertical extent of an edge is about 0.6*H*sqrt(2/NT) rows
+static int group_for_rows(double rows)
+{
     int g = 1;
-    while (g < 32 && rows / g > 8.0f) g <<= 1;
+    while (g < 32 && rows / g > 12.0) g <<= 1;
     return g;
 }
 
-template <int G, int TPB>
-static void launch_eval(const EvalJob* jobs, int njobs, int max_nt, int set, unsigned flags, double tol, cudaStream_t st)
+static int pick_group(const tpose_cuda_ctx* ctx, int NT, int H)
 {
-    const dim3 grid((max_nt + TPB - 1) / TPB, njobs);
-    k_eval<G, TPB><<<grid, EvalCfg<G, TPB>::kThreads, 0, st>>>(jobs, set, flags, tol);
+    if (valid_group(ctx->group)) return ctx->group;
+    return group_for_rows(0.6 * (double)H * sqrt(2.0 / (double)NT));
 }
 
-static void launch_eval_group(int group, const EvalJob* jobs, int njobs, int max_nt, int set, unsigned flags, double tol, cudaStream_t st)
+// 32-bit colour sums are exact while 255*W*H < 2^31
+static bool narrow_sums(int W, int H) { return 255ll * W * H < (1ll << 31); }
+
+constexpr int kMaxGridBlocks = 148 * 4;
+
+static int quantised_grid(long long blocks_needed)
 {
-    switch (group) {
-    case 1: launch_eval<1, 8>(jobs, njobs, max_nt, set, flags, tol, st); break;
-    case 2: launch_eval<2, 4>(jobs, njobs, max_nt, set, flags, tol, st); break;
-    case 4: launch_eval<4, 2>(jobs, njobs, max_nt, set, flags, tol, st); break;
-    case 8: launch_eval<8, 1>(jobs, njobs, max_nt, set, flags, tol, st); break;
-    case 16: launch_eval<16, 1>(jobs, njobs, max_nt, set, flags, tol, st); break;
-    default: launch_eval<32, 1>(jobs, njobs, max_nt, set, flags, tol, st); break;
+    int g = 32;
+    while (g < blocks_needed && g < kMaxGridBlocks) g <<= 1;
+    return g < kMaxGridBlocks ? g : kMaxGridBlocks;
+}
+
+static EvalShape make_shape(int group, int max_np, int max_ne, bool narrow)
+{
+    const int per_block = kEdgeThreads / group;
+    return EvalShape{group, quantised_grid(((long long)max_ne * kEdgeMoves + per_block - 1) / per_block),
+                     quantised_grid((max_np + kCornerWarps - 1) / kCornerWarps), narrow};
+}
+
+template <int G>
+static void launch_edges(const EvalJob* jobs, int njobs, const EvalShape& sh, int set, unsigned flags, double tol, cudaStream_t st)
+{
+    const dim3 grid(sh.grid_e + 1, njobs);   // + the service block
+    if (sh.narrow) k_edges<G, unsigned><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol);
+    else k_edges<G, unsigned long long><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol);
+}
+
+// one evaluation of every job: k_edges then k_corners
+static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int set, unsigned flags, double tol, cudaStream_t st,
+                        cudaEvent_t mid = nullptr)
+{
+    switch (sh.group) {
+    case 1: launch_edges<1>(jobs, njobs, sh, set, flags, tol, st); break;
+    case 2: launch_edges<2>(jobs, njobs, sh, set, flags, tol, st); break;
+    case 4: launch_edges<4>(jobs, njobs, sh, set, flags, tol, st); break;
+    case 8: launch_edges<8>(jobs, njobs, sh, set, flags, tol, st); break;
+    case 16: launch_edges<16>(jobs, njobs, sh, set, flags, tol, st); break;
+    default: launch_edges<32>(jobs, njobs, sh, set, flags, tol, st); break;
     }
+    if (mid) cudaEventRecord(mid, st);
+    k_corners<<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags);
+}
+constexpr int kLaunchesPerEval = 2;
+
+// ---- sequences of evaluations, replayed as CUDA graphs ------------------------------------------
+// A sequence is `len` evaluations into alternating buffer sets starting at `first_set`.
+//   kind 0 (step): every evaluation carries `flags`
+//   kind 1 (run):  evaluation 0 carries `flags`, the others add EV_CHECK_PREV, the last EV_FINAL
+// The host cannot issue two launches per step as fast as the device retires them, so sequences of
+// kGraphMinLen or more evaluations are captured once and replayed; the job records are read from
+// device memory at run time, so a captured sequence does not depend on the mesh or the image.
+constexpr int kGraphMinLen = 4;
+constexpr size_t kGraphCacheSize = 24;
+
+static void issue_direct(const SeqKey& k, cudaStream_t st, cudaEvent_t mid = nullptr)
+{
+    for (int j = 0; j < k.len; j++) {
+        unsigned f = k.flags;
+        if (k.kind == 1) {
+            if (j > 0) f |= EV_CHECK_PREV;
+            if (j == k.len - 1) f |= EV_FINAL;
+        }
+        launch_eval(k.shape, k.jobs, k.njobs, (k.first_set + j) & 1, f, k.tol, st, mid);
+    }
+}
+
+static bool same_key(const SeqKey& a, const SeqKey& b)
+{
+    return a.jobs == b.jobs && a.njobs == b.njobs && a.kind == b.kind && a.len == b.len && a.first_set == b.first_set &&
+           a.flags == b.flags && a.tol == b.tol && a.shape.group == b.shape.group && a.shape.grid_e == b.shape.grid_e &&
+           a.shape.grid_t == b.shape.grid_t && a.shape.narrow == b.shape.narrow;
+}
+
+static int issue_sequence(tpose_cuda_ctx* ctx, const SeqKey& key)
+{
+    ctx->launches += (int64_t)kLaunchesPerEval * key.len;
+    if (key.len < kGraphMinLen || !ctx->use_graphs) {
+        issue_direct(key, ctx->stream, key.len == 1 ? ctx->ev_mid : nullptr);
+        ctx->mid_valid = key.len == 1;
+        CK(cudaGetLastError());
+        return TPOSE_OK;
+    }
+    ctx->mid_valid = false;
+    ctx->graph_clock++;
+    for (auto& g : ctx->graphs)
+        if (same_key(g.key, key)) {
+            g.stamp = ctx->graph_clock;
+            CK(cudaGraphLaunch(g.exec, ctx->stream));
+            return TPOSE_OK;
+        }
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+        issue_direct(key, ctx->stream);
+        e = cudaStreamEndCapture(ctx->stream, &graph);
+    }
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {          // no graphs on this stream (e.g. it is being captured by the caller): launch directly
+        (void)cudaGetLastError();
+        ctx->use_graphs = false;
+        issue_direct(key, ctx->stream);
+        CK(cudaGetLastError());
+        return TPOSE_OK;
+    }
+    if (ctx->graphs.size() >= kGraphCacheSize) {
+        size_t oldest = 0;
+        for (size_t i = 1; i < ctx->graphs.size(); i++) if (ctx->graphs[i].stamp < ctx->graphs[oldest].stamp) oldest = i;
+        cudaGraphExecDestroy(ctx->graphs[oldest].exec);
+        ctx->graphs.erase(ctx->graphs.begin() + (long)oldest);
+    }
+    ctx->graphs.push_back(SeqGraph{key, exec, ctx->graph_clock});
+    CK(cudaGraphLaunch(exec, ctx->stream));
+    return TPOSE_OK;
+}
+
+// `nsteps` plain steps: even-length graph chunks (the set parity is the same after each), then singles
+static int issue_steps(tpose_cuda_ctx* ctx, const EvalJob* jobs, int njobs, const EvalShape& sh, unsigned flags, int first_set, int nsteps)
+{
+    int left = nsteps, set = first_set;
+    for (int chunk : {64, 16, 4})
+        while (left >= chunk) {
+            int rc = issue_sequence(ctx, SeqKey{jobs, njobs, sh, 0, chunk, set, flags, 0.0});
+            if (rc) return rc;
+            left -= chunk;
+        }
+    if (left > 0) {
+        int rc = issue_sequence(ctx, SeqKey{jobs, njobs, sh, 0, left, set, flags, 0.0});
+        if (rc) return rc;
+    }
+    return TPOSE_OK;
 }
 
 // the job record of this context for (slot, flavour)
@@ -303,22 +548,26 @@ static EvalJob make_job(const tpose_cuda_ctx* ctx, int slot, int flavour)
     EvalJob j;
     memset(&j, 0, sizeof j);
     j.table = s.table; j.pitch = s.pitch; j.W = s.W; j.H = s.H;
-    j.pts = ctx->pts; j.tri = ctx->tri; j.NT = ctx->NT; j.NP = ctx->NP;
+    j.pts = ctx->pts; j.tri = ctx->tri; j.NT = ctx->NT; j.NP = ctx->NP; j.NE = ctx->NE;
+    j.edges = ctx->edges; j.tri_edges = ctx->tri_edges; j.corner_off = ctx->corner_off; j.corners = ctx->corners;
+    j.rec = ctx->rec;
     j.ratio = ctx->ratio;
     j.dp = dp_for(ctx->NT, flavour);
     j.step = flavour == TPOSE_WARP ? 0.00003f : 0.00005f;
     for (int k = 0; k < 2; k++) { j.cn[k] = ctx->cn[k]; j.ca[k] = ctx->ca[k]; j.ten[k] = ctx->ten[k]; }
-    j.gr = ctx->gr; j.gr_acc = ctx->gr_acc;
+    j.gr = ctx->gr;
     j.wtri = ctx->watching ? ctx->wtri : nullptr;
     j.whe = ctx->watching ? ctx->whe : nullptr;
     j.err_state = ctx->err_state; j.run_state = ctx->run_state;
-    j.trig = ctx->ticket + 1; j.ticket = ctx->ticket;
+    j.trig = ctx->ticket + 1;
     return j;
 }
 
 // make job_dev current (a 200-byte copy, only when something changed)
 static int sync_job(tpose_cuda_ctx* ctx, int slot, int flavour)
 {
+    int rc = rebuild_edges(ctx);
+    if (rc) return rc;
     const EvalJob j = make_job(ctx, slot, flavour);
     if (!ctx->job_valid || memcmp(&j, &ctx->job_host, sizeof j) != 0) {
         ctx->job_host = j;
@@ -328,14 +577,19 @@ static int sync_job(tpose_cuda_ctx* ctx, int slot, int flavour)
     return TPOSE_OK;
 }
 
+static EvalShape shape_of(const tpose_cuda_ctx* ctx, int slot)
+{
+    const ImageSlot& im = ctx->img[slot];
+    return make_shape(pick_group(ctx, ctx->NT, im.H), ctx->NP, ctx->NE, narrow_sums(im.W, im.H));
+}
+
 static int eval(tpose_cuda_ctx* ctx, int slot, int flavour, int set, unsigned flags, double tol = 0.0)
 {
     int rc = sync_job(ctx, slot, flavour);
     if (rc) return rc;
-    launch_eval_group(pick_group(ctx, ctx->NT, ctx->img[slot].H), ctx->job_dev, 1, ctx->NT, set, flags, tol, ctx->stream);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return TPOSE_OK;
+    rc = issue_sequence(ctx, SeqKey{ctx->job_dev, 1, shape_of(ctx, slot), 0, 1, set, flags, tol});
+    ctx->mid_valid = false;      // only tpose_cuda_step brackets its kernels with events
+    return rc;
 }
 
 static int check_ready(tpose_cuda_ctx* ctx, int slot, int flavour)
@@ -394,29 +648,21 @@ extern "C" int tpose_cuda_step(tpose_cuda_ctx* ctx, int slot, int flavour, int n
     rc = sync_job(ctx, slot, flavour);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    const unsigned fl = fused_flags(flavour);
-    for (int i = 0; i < nsteps; i++) {
-        ctx->cur ^= 1;
-        rc = eval(ctx, slot, flavour, ctx->cur, fl);
-        if (rc) return rc;
-    }
+    rc = issue_steps(ctx, ctx->job_dev, 1, shape_of(ctx, slot), fused_flags(flavour), ctx->cur ^ 1, nsteps);
+    if (rc) return rc;
+    ctx->cur = (ctx->cur + nsteps) & 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     return TPOSE_OK;
 }
 
 // Launch j evaluates the points after j shifts into set (first+j)&1 and carries the checks of frame
 // j-1; launch max_steps is check-only.  See eval.cuh.
-static void issue_run(tpose_cuda_ctx* lead, const EvalJob* jobs, int njobs, int max_nt, int group, int first_set,
-                      int flavour, int max_steps, double rel_tol)
+// Evaluation j works on the points after j shifts, writes set (first+j)&1 and carries the checks of
+// frame j-1; evaluation max_steps is check-only.  See eval.cuh.
+static int issue_run(tpose_cuda_ctx* lead, const EvalJob* jobs, int njobs, const EvalShape& sh, int first_set,
+                     int flavour, int max_steps, double rel_tol)
 {
-    const unsigned fl = fused_flags(flavour) | EV_HONOUR_STOP;
-    for (int j = 0; j <= max_steps; j++) {
-        unsigned f = fl;
-        if (j > 0) f |= EV_CHECK_PREV;
-        if (j == max_steps) f |= EV_FINAL;
-        launch_eval_group(group, jobs, njobs, max_nt, (first_set + j) & 1, f, rel_tol, lead->stream);
-        lead->launches++;
-    }
+    return issue_sequence(lead, SeqKey{jobs, njobs, sh, 1, max_steps + 1, first_set, fused_flags(flavour) | EV_HONOUR_STOP, rel_tol});
 }
 
 extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int max_steps, double rel_tol,
@@ -430,8 +676,8 @@ extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int ma
     CK(cudaMemsetAsync(ctx->run_state, 0, sizeof(int) * 4, ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     const int first = ctx->cur ^ 1;
-    issue_run(ctx, ctx->job_dev, 1, ctx->NT, pick_group(ctx, ctx->NT, ctx->img[slot].H), first, flavour, max_steps, rel_tol);
-    CK(cudaGetLastError());
+    rc = issue_run(ctx, ctx->job_dev, 1, shape_of(ctx, slot), first, flavour, max_steps, rel_tol);
+    if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     int rs[4]; float es[4];
     CK(cudaMemcpyAsync(rs, ctx->run_state, sizeof rs, cudaMemcpyDeviceToHost, ctx->stream));
@@ -483,13 +729,13 @@ extern "C" int tpose_cuda_watch(tpose_cuda_ctx* ctx, const int32_t* tri_xyzw, co
 
 // ---- batches ---------------------------------------------------------------------------------
 
-static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, int flavour, int* max_nt, int* group)
+static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, int flavour, EvalShape* shape)
 {
     if (!ctxs || n < 1 || !ctxs[0]) return TPOSE_ERR_ARG;
     tpose_cuda_ctx* lead = ctxs[0];
     tpose_cuda_ctx* ctx = lead;   // for CK
     std::vector<EvalJob> jobs((size_t)n);
-    int mx = 0; double rows = 0.0;
+    int mxp = 0, mxe = 0; double rows = 0.0; bool narrow = true;
     for (int i = 0; i < n; i++) {
         const int slot = slots ? slots[i] : 0;
         int rc = check_ready(ctxs[i], slot, flavour);
@@ -497,8 +743,12 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
         if (ctxs[i]->device != lead->device) return fail(lead, TPOSE_ERR_ARG, "batch: contexts live on different devices");
         for (int k = 0; k < i; k++) if (ctxs[k] == ctxs[i]) return fail(lead, TPOSE_ERR_ARG, "batch: a context appears twice");
         if (ctxs[i] != lead) cudaStreamSynchronize(ctxs[i]->stream);   // its uploads are done before we touch its buffers
+        rc = rebuild_edges(ctxs[i]);
+        if (rc) { if (ctxs[i] != lead) lead->err = "batch: job " + std::to_string(i) + ": " + ctxs[i]->err; return rc; }
         jobs[(size_t)i] = make_job(ctxs[i], slot, flavour);
-        mx = ctxs[i]->NT > mx ? ctxs[i]->NT : mx;
+        mxp = ctxs[i]->NP > mxp ? ctxs[i]->NP : mxp;
+        mxe = ctxs[i]->NE > mxe ? ctxs[i]->NE : mxe;
+        narrow = narrow && narrow_sums(ctxs[i]->img[slot].W, ctxs[i]->img[slot].H);
         rows += 0.6 * ctxs[i]->img[slot].H * sqrt(2.0 / ctxs[i]->NT);
     }
     if (lead->batch_cap < n) {
@@ -508,20 +758,14 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
     }
     CK(cudaMemcpyAsync(lead->batch_jobs, jobs.data(), sizeof(EvalJob) * n, cudaMemcpyHostToDevice, lead->stream));
     CK(cudaStreamSynchronize(lead->stream));   // `jobs` is a local
-    *max_nt = mx;
-    int g = lead->group;
-    if (!(g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32)) {
-        g = 1;
-        while (g < 32 && rows / n / g > 8.0) g <<= 1;
-    }
-    *group = g;
+    *shape = make_shape(valid_group(lead->group) ? lead->group : group_for_rows(rows / n), mxp, mxe, narrow);
     return TPOSE_OK;
 }
 
 extern "C" int tpose_cuda_batch_step(tpose_cuda_ctx* const* ctxs, int n, const int* slots, int flavour, int nsteps)
 {
-    int max_nt = 0, group = 1;
-    int rc = batch_prepare(ctxs, n, slots, flavour, &max_nt, &group);
+    EvalShape shape{};
+    int rc = batch_prepare(ctxs, n, slots, flavour, &shape);
     if (rc) return rc;
     tpose_cuda_ctx* ctx = ctxs[0];
     if (nsteps < 0) return fail(ctx, TPOSE_ERR_ARG, "batch_step: nsteps < 0");
@@ -529,14 +773,9 @@ extern "C" int tpose_cuda_batch_step(tpose_cuda_ctx* const* ctxs, int n, const i
     for (int i = 1; i < n; i++)
         if (ctxs[i]->cur != ctx->cur) return fail(ctx, TPOSE_ERR_STATE, "batch: contexts are out of step (mix of stepped and fresh contexts)");
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    const unsigned fl = fused_flags(flavour);
-    int cur = ctx->cur;
-    for (int s = 0; s < nsteps; s++) {
-        cur ^= 1;
-        launch_eval_group(group, ctx->batch_jobs, n, max_nt, cur, fl, 0.0, ctx->stream);
-        ctx->launches++;
-    }
-    CK(cudaGetLastError());
+    rc = issue_steps(ctx, ctx->batch_jobs, n, shape, fused_flags(flavour), ctx->cur ^ 1, nsteps);
+    if (rc) return rc;
+    const int cur = (ctx->cur + nsteps) & 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     for (int i = 0; i < n; i++) ctxs[i]->cur = cur;
     return TPOSE_OK;
@@ -545,8 +784,8 @@ extern "C" int tpose_cuda_batch_step(tpose_cuda_ctx* const* ctxs, int n, const i
 extern "C" int tpose_cuda_batch_run(tpose_cuda_ctx* const* ctxs, int n, const int* slots, int flavour, int max_steps,
                                     double rel_tol, int* steps_done, uint32_t* trigger_flags)
 {
-    int max_nt = 0, group = 1;
-    int rc = batch_prepare(ctxs, n, slots, flavour, &max_nt, &group);
+    EvalShape shape{};
+    int rc = batch_prepare(ctxs, n, slots, flavour, &shape);
     if (rc) return rc;
     tpose_cuda_ctx* ctx = ctxs[0];
     if (max_steps < 1) return fail(ctx, TPOSE_ERR_ARG, "batch_run: max_steps < 1");
@@ -555,8 +794,8 @@ extern "C" int tpose_cuda_batch_run(tpose_cuda_ctx* const* ctxs, int n, const in
     for (int i = 0; i < n; i++) CK(cudaMemsetAsync(ctxs[i]->run_state, 0, sizeof(int) * 4, ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     const int first = ctx->cur ^ 1;
-    issue_run(ctx, ctx->batch_jobs, n, max_nt, group, first, flavour, max_steps, rel_tol);
-    CK(cudaGetLastError());
+    rc = issue_run(ctx, ctx->batch_jobs, n, shape, first, flavour, max_steps, rel_tol);
+    if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     std::vector<int> rs((size_t)4 * n);
     for (int i = 0; i < n; i++)
@@ -653,6 +892,11 @@ extern "C" int tpose_cuda_write(tpose_cuda_ctx* ctx, int which, size_t first, si
     if (count == 0 || !dev) return TPOSE_OK;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync((char*)dev + elem * first, in, elem * count, cudaMemcpyHostToDevice, ctx->stream));
+    if (which == TPOSE_BUF_INDEX) {   // keep the host mirror the edge view is derived from
+        if (ctx->tri_host.size() < (size_t)4 * (first + count)) ctx->tri_host.resize((size_t)4 * (first + count), 0);
+        memcpy(ctx->tri_host.data() + 4 * first, in, elem * count);
+        ctx->edges_dirty = true;
+    }
     if (which == TPOSE_BUF_COLACC)   // both buffer sets see uploaded colours (warp flavour reads them every frame)
         CK(cudaMemcpyAsync((char*)ctx->ca[ctx->cur ^ 1] + elem * first, in, elem * count, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -684,6 +928,17 @@ extern "C" int tpose_cuda_last_elapsed_ms(tpose_cuda_ctx* ctx, float* ms)
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventSynchronize(ctx->ev1));
     CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_last_kernel_ms(tpose_cuda_ctx* ctx, float* edges_ms, float* corners_ms)
+{
+    if (!ctx || !edges_ms || !corners_ms) return TPOSE_ERR_ARG;
+    if (!ctx->mid_valid) return fail(ctx, TPOSE_ERR_STATE, "last_kernel_ms: the last call was not a single tpose_cuda_step(.., 1)");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(edges_ms, ctx->ev0, ctx->ev_mid));
+    CK(cudaEventElapsedTime(corners_ms, ctx->ev_mid, ctx->ev1));
     return TPOSE_OK;
 }
 

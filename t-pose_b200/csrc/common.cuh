@@ -88,6 +88,7 @@ struct EdgeWalk {
         r0 = max(r0, 0);
         r_end = min(r1, H);
         r = r0 + lane;
+        q = 0; dq = 0; rem = 0; den = 1; dr = 0;
         if (sign == 0 || r >= r_end) { r = r_end; return; }
         const int dy = hi - lo, dx = b.x - a.x;       // |.| <= 2^24
         const int m = 256 * r + 128 - lo;             // 0 <= m < 2^24

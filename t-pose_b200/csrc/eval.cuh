@@ -1,19 +1,28 @@
-// eval.cuh -- the fused evaluation kernel: for every triangle, the six pixel moments of all 13
-// finite-difference variants, from 27 edge integrals over the row-prefix moment table; then, as
-// the flags ask, cn / ca / ten in the reference SSBO layout, the gradient scatter and the vertex
-// update.  One launch replaces the two 13*NT-instance draws plus gradient.cs and shift.cs
-// (software/triangulate/main.cpp:121-155; shaders triangle.vs/.fs, gradient.cs, shift.cs).
+// eval.cuh -- the evaluation kernels of one optimisation step: for every triangle, the six pixel
+// moments of all 13 finite-difference variants from edge integrals over the row-prefix moment
+// table; then, as the flags ask, cn / ca / ten in the reference SSBO layout, the gradient scatter
+// and the vertex update.  Two launches replace the two 13*NT-instance draws plus gradient.cs and
+// shift.cs (software/triangulate/main.cpp:121-155; shaders triangle.vs/.fs, gradient.cs, shift.cs):
 //
-// A launch can also carry the host-side checks of the PREVIOUS frame (EV_CHECK_PREV), so that a
-// run of frames needs no host round trip and no serial check kernel between frames:
+//   k_edges  one work item per (unique mesh edge, move q): q = 0 the edge as it is, q = 1..4 its
+//            first end point moved by (+dp,0),(-dp,0),(0,+dp),(0,-dp), q = 5..8 its second one.
+//            An interior edge is shared by two triangles and its nine integrals serve both (with
+//            opposite sign), so the table is walked once per edge, not once per triangle side.
+//            Results go to a 48-byte record per item.
+//   k_corners one thread per (triangle, variant k): three records -> moments -> cn/ca/ten.  The
+//            moved variants are grouped by the vertex they move (one warp per vertex), so
+//            gradient.cs becomes a warp reduction and shift.cs follows in the same warp.
+//
+// A step can also carry the host-side checks of the PREVIOUS frame (EV_CHECK_PREV), so that a run
+// of frames needs no host round trip and no serial check between frames:
 //   * geterr (source/triangulation.hpp:653-674) over the previous frame's base energies, by one
-//     thread of block 0's service warp, overlapped with the edge walks of this launch;
+//     thread of k_edges' service block, overlapped with the edge walks;
 //   * a conservative test of the per-frame topology edits of software/triangulate/main.cpp:316-346
 //     (prune / >0.8*pi flip / short-edge collapse) on the host's ("watch") topology at the current
-//     points, by the service warps.
-// If either fires, the last block does NOT apply this launch's shift and raises the stop flag:
-// points, and the other buffer set, are then exactly what the reference holds after the frame
-// whose checks fired.  The evaluation done by this launch is speculative and discarded.
+//     points, by the other threads of the service block.
+// If either fires, k_corners does NOT apply this step's shift and raises the stop
+// flag: points, and the other buffer set, are then exactly what the reference holds after the
+// frame whose checks fired.  The evaluation done by this step is speculative and discarded.
 #pragma once
 #include "common.cuh"
 
@@ -26,9 +35,9 @@ enum EvalFlags : unsigned {
     EV_MEAN_STORED = 8u,   // mean colour comes from the ca/cn buffers, not from this pass
     EV_MEAN_DIVIDE = 16u,  // mean = ca/cn (triangulate, triangle.fs:40); else mean = ca (warp :49-50)
     EV_GRAD_SHIFT  = 32u,  // gradient.cs + shift.cs fused behind the energies
-    EV_CHECK_PREV  = 64u,  // previous frame's geterr + topology watch ride on this launch
-    EV_FINAL       = 128u, // last launch of a run: checks only, never shifts
-    EV_HONOUR_STOP = 256u  // launch is a no-op once the job's stop flag is up
+    EV_CHECK_PREV  = 64u,  // previous frame's geterr + topology watch ride on this step
+    EV_FINAL       = 128u, // last step of a run: checks only, never shifts
+    EV_HONOUR_STOP = 256u  // step is a no-op once the job's stop flag is up
 };
 
 // trigger bits (mirrors include/tpose_cuda.h)
@@ -37,6 +46,14 @@ constexpr int kTrigConverged = 1, kTrigMaxSteps = 2, kTrigTopology = 4;
 // run_state words
 enum { RS_STOP = 0, RS_STEPS = 1, RS_TRIG = 2, RS_SPARE = 3 };
 
+constexpr int kEdgeMoves = 9;        // per unique edge: as it is + 4 moves of each end point
+
+// signed integral of one (edge, move) item, in the direction first -> second end point
+struct __align__(16) EdgeRec {
+    long long r, g, b, s2;
+    int n, odd, pad0, pad1;
+};
+
 // Everything one image-step needs; lives in device memory so that a batch of independent jobs can
 // share one launch (blockIdx.y = job).
 struct EvalJob {
@@ -44,32 +61,21 @@ struct EvalJob {
     int pitch, W, H;
     float2* pts;
     const int4* tri;
-    int NT, NP;
+    int NT, NP, NE;
     float ratio, dp, step;
-    int* cn[2]; int4* ca[2]; int* ten[2];   // two buffer sets, alternating per launch
+    int* cn[2]; int4* ca[2]; int* ten[2];   // two buffer sets, alternating per step
     int2* gr;                  // pgradbuf as the reference sees it (written by the vertex update)
-    int2* gr_acc;              // accumulation scratch, zero between launches
+    const int2* edges;         // NE unique edges (first, second end point), derived from tri at upload
+    const int4* tri_edges;     // per triangle side j: edge id, bit 31 set if the side runs second -> first
+    const int* corner_off;     // NP+1 offsets into `corners`: the triangle corners that sit on each vertex
+    const int* corners;        // 3*NT entries, triangle << 2 | corner, grouped by vertex
+    EdgeRec* rec;              // NE*9 records
     const int4* wtri;          // watch topology (the host's triangles / halfedges), may be null
     const int* whe;
     float* err_state;          // [0] toterr [1] |relerr| [2] newerr [3] converged flag of the last check
     int* run_state;            // RS_*
     unsigned* trig;            // [0] topology trigger accumulator
-    unsigned* ticket;          // last-block election counter
 };
-
-template <int G>
-__device__ __forceinline__ void group_reduce(Moments& m)
-{
-#pragma unroll
-    for (int o = G >> 1; o > 0; o >>= 1) {
-        m.n   += __shfl_xor_sync(0xffffffffu, m.n, o);
-        m.odd += __shfl_xor_sync(0xffffffffu, m.odd, o);
-        m.r   += __shfl_xor_sync(0xffffffffu, m.r, o);
-        m.g   += __shfl_xor_sync(0xffffffffu, m.g, o);
-        m.b   += __shfl_xor_sync(0xffffffffu, m.b, o);
-        m.s2  += __shfl_xor_sync(0xffffffffu, m.s2, o);
-    }
-}
 
 // shift.cs:16-47 for one vertex; gx, gy are the integer gradient sums
 __device__ __forceinline__ float2 shift_vertex(float2 p, int gxi, int gyi, float ratio, float step)
@@ -171,188 +177,245 @@ __device__ void geterr_serial(const int* __restrict__ ten_base, int nt, float* s
     state[3] = ((double)fabsf(rel) < rel_tol) ? 1.0f : 0.0f;
 }
 
-// G lanes cooperate on one edge variant; TPB triangles per block; one extra service warp.
-template <int G, int TPB>
-struct EvalCfg {
-    static constexpr int kItems = TPB * kEdgeVariants;
-    static constexpr int kWork = ((kItems * G + 31) / 32) * 32;   // threads that walk edges
-    static constexpr int kThreads = kWork + 32;                   // + service warp
-};
+// ---- k_edges ----------------------------------------------------------------------------------
 
-template <int G, int TPB>
-__global__ void __launch_bounds__(EvalCfg<G, TPB>::kThreads)
-k_eval(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_tol)
+constexpr int kEdgeThreads = 256;
+
+template <typename T> __device__ __forceinline__ T shfl_xor_any(T v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+
+// Walks the rows of one edge (this lane's share: rows r, r+G, ...) and sums the table entries at
+// the crossings.  ACC is the accumulator type of the three colour sums: 32 bits are enough when
+// 255*W*H < 2^31 (every image up to 3840x2160), else 64.
+template <int G, typename ACC>
+__device__ __forceinline__ void walk_edge(EdgeWalk& w, const uint4* __restrict__ table, int pitch, int W,
+                                          unsigned& n, unsigned& odd, ACC& sr, ACC& sg, ACC& sb, unsigned long long& s2)
 {
-    using Cfg = EvalCfg<G, TPB>;
-    constexpr int kItems = Cfg::kItems;
-    __shared__ EvalJob J;
-    __shared__ int2 s_fx[TPB][3][5];            // snapped vertices: [triangle][corner][0 base,1..4 moved]
-    __shared__ long long s_edge[kItems][4];     // signed edge integrals: r, g, b, s2
-    __shared__ int s_edge_n[kItems][2];         //                        n, odd
-    __shared__ int s_ten[TPB][kVariants];
-    __shared__ int4 s_tri[TPB];
-    __shared__ bool s_last;
+    int row = w.r * pitch;                     // entry index: (W+1)*H <= 4096*8192 fits 32 bits
+    const int rstep = G * pitch;
+    const int r_end = w.r_end;
+    int rr = w.r, q = w.q;
+    const int dq = w.dq;
+    if (w.den < (1ll << 30)) {                 // every on-screen edge: remainders fit 32 bits
+        int rem = (int)w.rem;
+        const int den = (int)w.den, dr = (int)w.dr;
+#pragma unroll 4
+        for (; rr < r_end; rr += G) {
+            const int c = min(max(q, 0), W);
+            const uint4 e = __ldg(table + (row + c));
+            n += (unsigned)c; odd += e.x >> 20; sr += (ACC)(e.x & 0xFFFFFu); sg += (ACC)e.y; sb += (ACC)e.z; s2 += e.w;
+            q += dq; rem += dr;
+            if (rem >= den) { rem -= den; ++q; }
+            row += rstep;
+        }
+    } else {
+        long long rem = w.rem;
+        const long long den = w.den, dr = w.dr;
+        for (; rr < r_end; rr += G) {
+            const int c = min(max(q, 0), W);
+            const uint4 e = __ldg(table + (row + c));
+            n += (unsigned)c; odd += e.x >> 20; sr += (ACC)(e.x & 0xFFFFFu); sg += (ACC)e.y; sb += (ACC)e.z; s2 += e.w;
+            q += dq; rem += dr;
+            if (rem >= den) { rem -= den; ++q; }
+            row += rstep;
+        }
+    }
+}
 
+// G lanes per (edge, move) item.  The last block of each job's row is the service block.
+template <int G, typename ACC>
+__global__ void __launch_bounds__(kEdgeThreads)
+k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_tol)
+{
+    __shared__ EvalJob J;
     const int tid = threadIdx.x;
     if (tid < (int)(sizeof(EvalJob) / sizeof(int)))
         reinterpret_cast<int*>(&J)[tid] = reinterpret_cast<const int*>(jobs + blockIdx.y)[tid];
     __syncthreads();
-    const int nblocks = (J.NT + TPB - 1) / TPB;
-    if ((int)blockIdx.x >= nblocks) return;
     if ((flags & EV_HONOUR_STOP) && __ldcg(&J.run_state[RS_STOP])) return;
-    const int t0 = blockIdx.x * TPB;
+
+    if (blockIdx.x == gridDim.x - 1) {
+        // service block: the previous frame's host-side checks
+        if (!(flags & EV_CHECK_PREV)) return;
+        if (tid == 0) *J.trig = 0u;
+        __syncthreads();
+        if (tid == kEdgeThreads - 1) geterr_serial(J.ten[set ^ 1], J.NT, J.err_state, rel_tol);
+        else if (J.wtri) {
+            bool hit = false;
+            for (int t = tid; t < J.NT; t += kEdgeThreads - 1) hit |= watch_triangle(J, t);
+            if (hit) atomicOr(J.trig, (unsigned)kTrigTopology);
+        }
+        return;
+    }
+
+    constexpr int kItemsPerBlock = kEdgeThreads / G;
+    const int lane = tid % G;
+    const int nitems = J.NE * kEdgeMoves;
+    const Xform xf{J.ratio, 0.5f * (float)J.W, 0.5f * (float)J.H, 256 * J.H};
+    // the grid does not depend on the mesh size (so a captured graph survives topology changes):
+    // blocks stride over the items
+    for (int base = blockIdx.x * kItemsPerBlock; base < nitems; base += (gridDim.x - 1) * kItemsPerBlock) {
+        const int item = base + tid / G;
+        unsigned n = 0, odd = 0; ACC sr = 0, sg = 0, sb = 0; unsigned long long s2 = 0;
+        int sign = 0;
+        if (item < nitems) {
+            const int e = item / kEdgeMoves, q = item - e * kEdgeMoves;
+            const int2 ev = __ldg(J.edges + e);
+            const float2 pa = J.pts[ev.x], pb = J.pts[ev.y];
+            float dxa = 0.0f, dya = 0.0f, dxb = 0.0f, dyb = 0.0f;
+            if (q >= 1 && q <= 4) fd_offset(q - 1, J.dp, dxa, dya);
+            if (q >= 5) fd_offset(q - 5, J.dp, dxb, dyb);
+            const int2 a = to_fixed(pa, dxa, dya, xf), b = to_fixed(pb, dxb, dyb, xf);
+            EdgeWalk w;
+            w.init(a, b, J.H, lane, G);
+            sign = w.sign;
+            walk_edge<G, ACC>(w, J.table, J.pitch, J.W, n, odd, sr, sg, sb, s2);
+        }
+#pragma unroll
+        for (int o = G >> 1; o > 0; o >>= 1) {
+            n += shfl_xor_any(n, o); odd += shfl_xor_any(odd, o);
+            sr += shfl_xor_any(sr, o); sg += shfl_xor_any(sg, o); sb += shfl_xor_any(sb, o); s2 += shfl_xor_any(s2, o);
+        }
+        if (item < nitems && lane == 0) {
+            EdgeRec rec;
+            rec.r = sign * (long long)sr; rec.g = sign * (long long)sg; rec.b = sign * (long long)sb;
+            rec.s2 = sign * (long long)s2;
+            rec.n = sign * (int)n; rec.odd = sign * (int)odd; rec.pad0 = 0; rec.pad1 = 0;
+            J.rec[item] = rec;
+        }
+    }
+}
+
+// ---- k_corners ----------------------------------------------------------------------------------
+// Variant k = 1+4j+s of triangle t moves corner j, and only the vertex at that corner reads its
+// energy (gradient.cs:27-34).  So the 12 moved variants of every triangle are evaluated grouped by
+// VERTEX: one warp per vertex walks the vertex's corner list (built at upload), four lanes per
+// corner (s = 0..3), and the central differences are summed inside the warp -- no atomics, no
+// fences, no inter-block ordering.  The base variants (k = 0) go to the remaining blocks.
+
+constexpr int kCornerThreads = 256;
+constexpr int kCornerWarps = kCornerThreads / 32;
+constexpr int kBaseBlocks = 16;          // blocks at the end of the grid that take the base variants
+
+__device__ __forceinline__ void add_rec(const EdgeRec* __restrict__ recs, int packed, int qlocal,
+                                        long long& sr, long long& sg, long long& sb, long long& s2, int& n, int& odd)
+{
+    // side runs second -> first: its first corner is the edge's second end point, and the sign flips
+    const bool rev = packed < 0;
+    const int e = packed & 0x7fffffff;
+    const int q = (rev && qlocal) ? (qlocal <= 4 ? qlocal + 4 : qlocal - 4) : qlocal;
+    const longlong2* p = reinterpret_cast<const longlong2*>(recs + (size_t)e * kEdgeMoves + q);
+    const longlong2 v0 = __ldcg(p), v1 = __ldcg(p + 1);
+    const int2 v2 = __ldcg(reinterpret_cast<const int2*>(p + 2));
+    if (rev) { sr -= v0.x; sg -= v0.y; sb -= v1.x; s2 -= v1.y; n -= v2.x; odd -= v2.y; }
+    else     { sr += v0.x; sg += v0.y; sb += v1.x; s2 += v1.y; n += v2.x; odd += v2.y; }
+}
+
+// variant k of triangle t: three edge records -> moments -> cn / ca / ten as the flags ask.
+// Returns the (wrapped int32) energy.
+__device__ __forceinline__ int eval_variant(const EvalJob& J, unsigned flags, int* __restrict__ cn, int4* __restrict__ ca,
+                                            int* __restrict__ ten, int t, int k)
+{
+    const int4 te = __ldg(J.tri_edges + t);
+    // side j has its first corner moved, side j+2 its second one; the third side is as it is
+    const int j = (k - 1) >> 2, s = (k - 1) & 3, j2 = (j >= 1) ? j - 1 : 2;
+    const int q0 = (k == 0) ? 0 : (j == 0 ? 1 + s : (j2 == 0 ? 5 + s : 0));
+    const int q1 = (k == 0) ? 0 : (j == 1 ? 1 + s : (j2 == 1 ? 5 + s : 0));
+    const int q2 = (k == 0) ? 0 : (j == 2 ? 1 + s : (j2 == 2 ? 5 + s : 0));
+    long long sr = 0, sg = 0, sb = 0, s2 = 0; int n = 0, odd = 0;
+    add_rec(J.rec, te.x, q0, sr, sg, sb, s2, n, odd);
+    add_rec(J.rec, te.y, q1, sr, sg, sb, s2, n, odd);
+    add_rec(J.rec, te.z, q2, sr, sg, sb, s2, n, odd);
+    if (n < 0) { n = -n; odd = -odd; sr = -sr; sg = -sg; sb = -sb; s2 = -s2; }
+    const int g = k * J.NT + t;
+    if (flags & EV_WRITE_CN) cn[g] = n;
+    if (flags & EV_WRITE_CA) ca[g] = make_int4((int)sr, (int)sg, (int)sb, 0);
+    int e32 = 0;
+    if (flags & EV_WRITE_TEN) {
+        int m0 = 0, m1 = 0, m2 = 0; bool have = true;
+        if (flags & EV_MEAN_STORED) {
+            const int4 c = ca[g];
+            if (flags & EV_MEAN_DIVIDE) {
+                const int cnt = cn[g];
+                if (cnt > 0) { m0 = c.x / cnt; m1 = c.y / cnt; m2 = c.z / cnt; } else have = false;
+            } else { m0 = c.x; m1 = c.y; m2 = c.z; }
+        } else {
+            // |sums| <= 255*n < 2^31 here, so the quotient is a 32-bit one unless an accumulator
+            // would have wrapped -- then take the general path
+            if (n > 0) {
+                if (sr == (int)sr && sg == (int)sg && sb == (int)sb) { m0 = (int)sr / n; m1 = (int)sg / n; m2 = (int)sb / n; }
+                else { m0 = (int)(sr / n); m1 = (int)(sg / n); m2 = (int)(sb / n); }
+            } else have = false;
+        }
+        const long long e = have ? energy_closed_form(n, odd, sr, sg, sb, s2, m0, m1, m2) : 0ll;
+        e32 = (int)(unsigned)(unsigned long long)e;   // int32 accumulator wraps
+        ten[g] = e32;
+    }
+    return e32;
+}
+
+__global__ void __launch_bounds__(kCornerThreads)
+k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags)
+{
+    __shared__ EvalJob J;
+    const int tid = threadIdx.x;
+    if (tid < (int)(sizeof(EvalJob) / sizeof(int)))
+        reinterpret_cast<int*>(&J)[tid] = reinterpret_cast<const int*>(jobs + blockIdx.y)[tid];
+    __syncthreads();
+    // RS_STOP is raised by this kernel's first block only when this very launch decided to stop;
+    // a block that sees it then skips work that is discarded anyway
+    if ((flags & EV_HONOUR_STOP) && __ldcg(&J.run_state[RS_STOP])) return;
     int* const cn = J.cn[set]; int4* const ca = J.ca[set]; int* const ten = J.ten[set];
 
-    // phase 0: snapped positions of the 15 (corner, move) combinations of each triangle
-    if (tid < TPB * 15) {
-        const int tb = tid / 15, j = (tid % 15) / 5, s5 = tid % 5;
-        const int t = t0 + tb;
-        if (t < J.NT) {
-            const int4 tv = J.tri[t];
-            if (j == 0 && s5 == 0) s_tri[tb] = tv;
-            const int v = (j == 0) ? tv.x : (j == 1) ? tv.y : tv.z;
-            const float2 pv = J.pts[v];
-            float dx = 0.0f, dy = 0.0f;
-            if (s5 > 0) fd_offset(s5 - 1, J.dp, dx, dy);
-            Xform xf{J.ratio, 0.5f * (float)J.W, 0.5f * (float)J.H, 256 * J.H};
-            s_fx[tb][j][s5] = to_fixed(pv, dx, dy, xf);
-        }
+    const int nvb = (int)gridDim.x - kBaseBlocks;           // blocks that take vertices
+    if ((int)blockIdx.x >= nvb) {
+        // base variants, one thread each
+        for (int t = ((int)blockIdx.x - nvb) * kCornerThreads + tid; t < J.NT; t += kBaseBlocks * kCornerThreads)
+            eval_variant(J, flags, cn, ca, ten, t, 0);
+        return;
     }
-    __syncthreads();
 
-    if (tid < Cfg::kWork) {
-        // phase 1: edge integrals.  item = (triangle, edge e, move q): q=0 base, 1..4 corner e moved,
-        // 5..8 corner e+1 moved.
-        const int it = tid / G, lane = tid % G;
-        Moments m; m.zero();
-        int sign = 0;
-        if (it < kItems) {
-            const int tb = it / kEdgeVariants, ev = it % kEdgeVariants;
-            const int e = ev / 9, q = ev % 9;
-            if (t0 + tb < J.NT) {
-                const int ja = e, jb = (e + 1) % 3;
-                const int2 a = s_fx[tb][ja][(q >= 1 && q <= 4) ? q : 0];
-                const int2 b = s_fx[tb][jb][(q >= 5) ? q - 4 : 0];
-                EdgeWalk w;
-                w.init(a, b, J.H, lane, G);
-                sign = w.sign;
-                const uint4* __restrict__ table = J.table;
-                const int pitch = J.pitch, W = J.W;
-#pragma unroll 4
-                while (!w.done()) {
-                    const int c = w.cross(W);
-                    const uint4 en = __ldg(table + (size_t)w.r * pitch + c);
-                    m.add_entry(en, c);
-                    w.next(G);
-                }
-            }
-        }
-        group_reduce<G>(m);
-        if (it < kItems && lane == 0) {
-            s_edge[it][0] = sign * m.r;  s_edge[it][1] = sign * m.g;
-            s_edge[it][2] = sign * m.b;  s_edge[it][3] = sign * m.s2;
-            s_edge_n[it][0] = sign * m.n; s_edge_n[it][1] = sign * m.odd;
-        }
-    } else if (flags & EV_CHECK_PREV) {
-        // service warp: the previous frame's host-side checks
-        const int sl = tid - Cfg::kWork;
-        if (blockIdx.x == 0 && sl == 31) geterr_serial(J.ten[set ^ 1], J.NT, J.err_state, rel_tol);
-        if (J.wtri && sl < TPB && t0 + sl < J.NT && watch_triangle(J, t0 + sl)) atomicOr(J.trig, (unsigned)kTrigTopology);
-    }
-    __syncthreads();
-
-    // phase 2: one thread per (triangle, variant k): three edge integrals -> moments -> outputs
-    if (tid < TPB * kVariants) {
-        const int tb = tid / kVariants, k = tid % kVariants;
-        const int t = t0 + tb;
-        if (t < J.NT) {
-            int i0, i1, i2;
-            const int base = tb * kEdgeVariants;
-            if (k == 0) { i0 = base; i1 = base + 9; i2 = base + 18; }
-            else {
-                const int j = (k - 1) >> 2, s = (k - 1) & 3;
-                i0 = base + 9 * j + 1 + s;                  // edge j   : its first corner moved
-                i1 = base + 9 * ((j + 2) % 3) + 5 + s;      // edge j+2 : its second corner moved
-                i2 = base + 9 * ((j + 1) % 3);              // opposite edge, unchanged
-            }
-            long long sr = s_edge[i0][0] + s_edge[i1][0] + s_edge[i2][0];
-            long long sg = s_edge[i0][1] + s_edge[i1][1] + s_edge[i2][1];
-            long long sb = s_edge[i0][2] + s_edge[i1][2] + s_edge[i2][2];
-            long long s2 = s_edge[i0][3] + s_edge[i1][3] + s_edge[i2][3];
-            int n   = s_edge_n[i0][0] + s_edge_n[i1][0] + s_edge_n[i2][0];
-            int odd = s_edge_n[i0][1] + s_edge_n[i1][1] + s_edge_n[i2][1];
-            if (n < 0) { n = -n; odd = -odd; sr = -sr; sg = -sg; sb = -sb; s2 = -s2; }
-            const int g = k * J.NT + t;
-            if (flags & EV_WRITE_CN) cn[g] = n;
-            if (flags & EV_WRITE_CA) ca[g] = make_int4((int)sr, (int)sg, (int)sb, 0);
-            if (flags & EV_WRITE_TEN) {
-                int m0 = 0, m1 = 0, m2 = 0; bool have = true;
-                if (flags & EV_MEAN_STORED) {
-                    const int4 c = ca[g];
-                    if (flags & EV_MEAN_DIVIDE) {
-                        const int cnt = cn[g];
-                        if (cnt > 0) { m0 = c.x / cnt; m1 = c.y / cnt; m2 = c.z / cnt; } else have = false;
-                    } else { m0 = c.x; m1 = c.y; m2 = c.z; }
-                } else {
-                    if (n > 0) { m0 = (int)(sr / n); m1 = (int)(sg / n); m2 = (int)(sb / n); } else have = false;
-                }
-                const long long e = have ? energy_closed_form(n, odd, sr, sg, sb, s2, m0, m1, m2) : 0ll;
-                const int e32 = (int)(unsigned)(unsigned long long)e;   // int32 accumulator wraps
-                ten[g] = e32;
-                s_ten[tb][k] = e32;
-            }
-        }
-    }
-    if (!(flags & EV_GRAD_SHIFT)) return;
-    __syncthreads();
-
-    // phase 3: gradient.cs:27-34 -- central differences scattered to the three corners
-    if (tid < TPB * 3) {
-        const int tb = tid / 3, j = tid % 3;
-        const int t = t0 + tb;
-        if (t < J.NT) {
-            const int4 tv = s_tri[tb];
-            const int v = (j == 0) ? tv.x : (j == 1) ? tv.y : tv.z;
-            const unsigned gx = (unsigned)s_ten[tb][1 + 4 * j] - (unsigned)s_ten[tb][2 + 4 * j];
-            const unsigned gy = (unsigned)s_ten[tb][3 + 4 * j] - (unsigned)s_ten[tb][4 + 4 * j];
-            atomicAdd((unsigned*)&J.gr_acc[v].x, gx);
-            atomicAdd((unsigned*)&J.gr_acc[v].y, gy);
-        }
-    }
-    // phase 4: the last block of this job to get here owns the commit: either the vertex update
-    // (shift.cs) or, if the previous frame's checks fired, the stop.
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();      // cumulative: covers this block's writes and atomics (ordered by the barrier)
-        s_last = (atomicAdd(J.ticket, 1u) == (unsigned)nblocks - 1u);
-        if (s_last) __threadfence();
-    }
-    __syncthreads();
-    if (!s_last) return;
-    bool stop = false;
+    // the previous frame's verdict (written by k_edges' service block of this step)
+    bool stop = false, conv = false; unsigned topo = 0u;
     if (flags & EV_CHECK_PREV) {
-        const bool conv = __ldcg(&J.err_state[3]) != 0.0f;
-        const unsigned topo = __ldcg(J.trig);
+        conv = __ldcg(&J.err_state[3]) != 0.0f;
+        topo = __ldcg(J.trig);
         stop = conv || topo != 0u || (flags & EV_FINAL);
-        if (tid == 0) {
-            *J.trig = 0u;
-            if (stop) {
-                J.run_state[RS_STOP] = 1;
-                J.run_state[RS_TRIG] = (conv ? kTrigConverged : 0) | (topo ? kTrigTopology : 0) |
-                                       ((!conv && !topo) ? kTrigMaxSteps : 0);
-            }
+    }
+    if (blockIdx.x == 0 && tid == 0 && (flags & EV_GRAD_SHIFT)) {
+        if (stop) {
+            J.run_state[RS_STOP] = 1;
+            J.run_state[RS_TRIG] = (conv ? kTrigConverged : 0) | (topo ? kTrigTopology : 0) |
+                                   ((!conv && !topo) ? kTrigMaxSteps : 0);
+        } else {
+            J.run_state[RS_STEPS] += 1;
         }
     }
-    for (int v = tid; v < J.NP; v += blockDim.x) {
-        const int2 g = __ldcg(&J.gr_acc[v]);
-        J.gr_acc[v] = make_int2(0, 0);
-        if (stop) continue;
-        J.gr[v] = g;
-        if (v >= 4) J.pts[v] = shift_vertex(J.pts[v], g.x, g.y, J.ratio, J.step);
-    }
-    if (tid == 0) {
-        *J.ticket = 0u;
-        if (!stop) J.run_state[RS_STEPS] += 1;
+
+    const int lane = tid & 31, c_in = lane >> 2, s = lane & 3;
+    for (int v = (int)blockIdx.x * kCornerWarps + (tid >> 5); v < J.NP; v += nvb * kCornerWarps) {
+        const int c0 = __ldg(J.corner_off + v), c1 = __ldg(J.corner_off + v + 1);
+        float2 p = make_float2(0.0f, 0.0f);
+        if (lane == 0) p = J.pts[v];
+        unsigned gx = 0u, gy = 0u;
+        for (int cb = c0; cb < c1; cb += 8) {
+            const int c = cb + c_in;
+            if (c < c1) {
+                const int packed = __ldg(J.corners + c);          // triangle << 2 | corner
+                const int t = packed >> 2, j = packed & 3;
+                const unsigned e = (unsigned)eval_variant(J, flags, cn, ca, ten, t, 1 + 4 * j + s);
+                // gradient.cs:27-34: x from the +-dp moves in x (s = 0, 1), y from s = 2, 3
+                const unsigned signed_e = (s & 1) ? 0u - e : e;
+                if (s < 2) gx += signed_e; else gy += signed_e;
+            }
+        }
+        if (!(flags & EV_GRAD_SHIFT)) continue;
+        gx = __reduce_add_sync(0xffffffffu, gx);
+        gy = __reduce_add_sync(0xffffffffu, gy);
+        if (lane == 0 && !stop) {
+            // shift.cs:16-47 (vertices nothing references get a zero gradient and are still clamped)
+            J.gr[v] = make_int2((int)gx, (int)gy);
+            if (v >= 4) J.pts[v] = shift_vertex(p, (int)gx, (int)gy, J.ratio, J.step);
+        }
     }
 }
 
