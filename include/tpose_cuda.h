@@ -201,6 +201,11 @@ int64_t tpose_cuda_launch_count(const tpose_cuda_ctx *ctx);
  * row-major, scaled so that F(2,2) = 1.  An empty list yields the identity, like the reference. */
 int tpose_cuda_f8point(int device, const float *A_xy, const float *B_xy, const int *offsets, int nbatch,
                        float *F9_out);
+/* mview::F_Sampson (multiview.hpp:187-242; :244-299 when `weights` -- one float per match, same
+ * concatenation -- is non-NULL): the 8-point estimate, then `iterations` (the reference: 100)
+ * solves re-weighted by the Sampson denominators of the current estimate.  Same outputs as above. */
+int tpose_cuda_fsampson(int device, const float *A_xy, const float *B_xy, const float *weights,
+                        const int *offsets, int nbatch, int iterations, float *F9_out);
 /* mview::triangulate(F, K, A, B) (multiview.hpp:529-627): per match the Hartley-Sturm optimal
  * correction (:415-527; skipped if optimal_correction == 0), then HDLT (:370-380) against
  * PA = K[I|0], PB = K[R2|-t] from E = K^T F K (check = 3).  F9 / K9: one 3x3 per list.

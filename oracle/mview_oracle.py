@@ -206,3 +206,52 @@ def triangulate(F, K, A, B, correct=True):
         X = hdlt(KPA, KPB, A[i], B[i])
         out[i] = X / X[3]
     return out
+
+
+def eline(F, p):
+    """multiview.hpp:108-113: l = F (p,1) in float32 (glm mat3*vec3: products summed left to right),
+    divided by its z.  utility.hpp:146-153 (fromEigen3) is the identity on the mathematical matrix."""
+    F = np.asarray(F, f32)
+    x, y = f32(p[0]), f32(p[1])
+    l = np.array([f32(f32(f32(F[i, 0] * x) + f32(F[i, 1] * y)) + F[i, 2]) for i in range(3)], f32)
+    return (l / l[2]).astype(f32)
+
+
+def f_sampson(pa, pb, w=None, iters=100):
+    """multiview.hpp:187-242 (and :244-299 with per-match weights w): 100 re-weighted 8-point solves.
+    Kept literally, including the first iteration's mix of the DE-normalised initial F with the
+    normalised points (:189-205).  float32 where the reference stores floats, float64 LAPACK for
+    the decompositions.  Returns float64 (compare after casting to float32)."""
+    pa = np.asarray(pa, f32); pb = np.asarray(pb, f32)
+    F = f_8point(pa, pb).astype(f32)
+    if len(pa) != len(pb) or len(pa) == 0:
+        return F.astype(np.float64)
+    na, HA = normalize(pa)
+    nb, HB = normalize(pb)
+    n = len(na)
+    for _ in range(iters):
+        Ft = F.T.copy()
+        # vectorised eline for all matches (same float32 operation order as eline above)
+        def lines(M, P):
+            out = np.empty((n, 3), f32)
+            for i in range(3):
+                out[:, i] = ((M[i, 0] * P[:, 0]).astype(f32) + (M[i, 1] * P[:, 1]).astype(f32)).astype(f32) + M[i, 2]
+            return (out / out[:, 2:3]).astype(f32)
+        L = lines(Ft, nb)
+        R = lines(F, na)
+        den = (L[:, 0] * L[:, 0]).astype(f32)
+        den = (den + (L[:, 1] * L[:, 1]).astype(f32)).astype(f32)
+        den = (den + (R[:, 0] * R[:, 0]).astype(f32)).astype(f32)
+        den = (den + (R[:, 1] * R[:, 1]).astype(f32)).astype(f32)
+        W = (f32(1.0) / den).astype(f32)
+        if w is not None:
+            W = (np.asarray(w, f32) * W).astype(f32)
+        xa, ya, xb, yb = na[:, 0], na[:, 1], nb[:, 0], nb[:, 1]
+        cols = [((W * xa).astype(f32) * xb).astype(f32), ((W * ya).astype(f32) * xb).astype(f32), (W * xb).astype(f32),
+                ((W * xa).astype(f32) * yb).astype(f32), ((W * ya).astype(f32) * yb).astype(f32), (W * yb).astype(f32),
+                (W * xa).astype(f32), (W * ya).astype(f32), W]
+        A = np.stack(cols, 1).astype(np.float64)
+        _, _, Vt = np.linalg.svd(A, full_matrices=True)
+        F = _rank2(Vt[8].astype(f32).astype(np.float64).reshape(3, 3)).astype(f32)
+    Fd = HB.astype(np.float64).T @ F.astype(np.float64) @ HA.astype(np.float64)
+    return Fd / Fd[2, 2]

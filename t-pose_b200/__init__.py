@@ -43,7 +43,7 @@ EXPORTS = [
     "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
     "tpose_cuda_raster_ids", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_sync",
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
-    "tpose_cuda_f8point", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
+    "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
     "tpose_cuda_mview_last_ms",
     "tpose_cuda_watch", "tpose_cuda_read", "tpose_cuda_write", "tpose_cuda_batch_step", "tpose_cuda_batch_run",
 ]
@@ -270,6 +270,23 @@ def f8point(A_lists, B_lists, device=0):
         A = np.zeros((1, 2), np.float32); B = np.zeros((1, 2), np.float32)
     F = np.zeros((len(A_lists), 9), np.float32)
     _mview_ck(lib().tpose_cuda_f8point(device, _ptr(A), _ptr(B), _ptr(offs), len(A_lists), _ptr(F)), "f8point")
+    return F.reshape(-1, 3, 3)
+
+
+def fsampson(A_lists, B_lists, weights=None, iterations=100, device=0):
+    """Batched mview::F_Sampson (weights: list of (N_i,) float32 or None) -> (nbatch, 3, 3) float32."""
+    A, offs = _concat(A_lists)
+    B, offs_b = _concat(B_lists)
+    assert np.array_equal(offs, offs_b), "matched sets have different size"
+    W = None
+    if weights is not None:
+        W = np.ascontiguousarray(np.concatenate([np.asarray(w, np.float32).ravel() for w in weights]))
+        assert W.shape[0] == A.shape[0], "one weight per match"
+    if A.shape[0] == 0:
+        A = np.zeros((1, 2), np.float32); B = np.zeros((1, 2), np.float32); W = None
+    F = np.zeros((len(A_lists), 9), np.float32)
+    _mview_ck(lib().tpose_cuda_fsampson(device, _ptr(A), _ptr(B), _ptr(W), _ptr(offs), len(A_lists),
+                                        C.c_int(iterations), _ptr(F)), "fsampson")
     return F.reshape(-1, 3, 3)
 
 

@@ -1018,28 +1018,46 @@ bool offsets_ok(const int* offsets, int nbatch)
 extern "C" const char* tpose_cuda_mview_last_error(void) { return g_mview_error.c_str(); }
 extern "C" float tpose_cuda_mview_last_ms(void) { return g_mview_ms; }
 
-extern "C" int tpose_cuda_f8point(int device, const float* A_xy, const float* B_xy, const int* offsets, int nbatch, float* F9_out)
+static int fmatrix_common(int device, const float* A_xy, const float* B_xy, const int* offsets, int nbatch,
+                          const float* weights, int iters, float* F9_out, const char* who)
 {
-    if (!A_xy || !B_xy || !F9_out || !offsets_ok(offsets, nbatch)) return mview_fail(TPOSE_ERR_ARG, "f8point: bad arguments");
+    if (!A_xy || !B_xy || !F9_out || !offsets_ok(offsets, nbatch) || iters < 0)
+        return mview_fail(TPOSE_ERR_ARG, std::string(who) + ": bad arguments");
     int rc = mview_device(device);
     if (rc) return rc;
     const size_t n = (size_t)offsets[nbatch];
-    DevBuf dA, dB, dO, dF;
+    DevBuf dA, dB, dO, dF, dW;
     MCK(dA.alloc(n * sizeof(float2))); MCK(dB.alloc(n * sizeof(float2)));
     MCK(dO.alloc((nbatch + 1) * sizeof(int))); MCK(dF.alloc((size_t)nbatch * 9 * sizeof(float)));
     MCK(cudaMemcpy(dA.p, A_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
     MCK(cudaMemcpy(dB.p, B_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
     MCK(cudaMemcpy(dO.p, offsets, (nbatch + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    if (weights) {
+        MCK(dW.alloc(n * sizeof(float)));
+        MCK(cudaMemcpy(dW.p, weights, n * sizeof(float), cudaMemcpyHostToDevice));
+    }
     cudaEvent_t e0, e1;
     MCK(cudaEventCreate(&e0)); MCK(cudaEventCreate(&e1));
     MCK(cudaEventRecord(e0, 0));
-    k_f8point<<<nbatch, kF8Threads>>>(dA.as<float2>(), dB.as<float2>(), dO.as<int>(), dF.as<float>());
+    k_f8point<<<nbatch, kF8Threads>>>(dA.as<float2>(), dB.as<float2>(), dO.as<int>(), weights ? dW.as<float>() : nullptr, iters,
+                                      dF.as<float>());
     MCK(cudaEventRecord(e1, 0));
     MCK(cudaGetLastError());
     MCK(cudaMemcpy(F9_out, dF.p, (size_t)nbatch * 9 * sizeof(float), cudaMemcpyDeviceToHost));
     cudaEventElapsedTime(&g_mview_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_f8point(int device, const float* A_xy, const float* B_xy, const int* offsets, int nbatch, float* F9_out)
+{
+    return fmatrix_common(device, A_xy, B_xy, offsets, nbatch, nullptr, 0, F9_out, "f8point");
+}
+
+extern "C" int tpose_cuda_fsampson(int device, const float* A_xy, const float* B_xy, const float* weights, const int* offsets,
+                                   int nbatch, int iterations, float* F9_out)
+{
+    return fmatrix_common(device, A_xy, B_xy, offsets, nbatch, weights, iterations, F9_out, "fsampson");
 }
 
 extern "C" int tpose_cuda_triangulate(int device, const float* F9, const float* K9, const float* A_xy, const float* B_xy,

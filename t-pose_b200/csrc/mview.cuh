@@ -64,35 +64,123 @@ __device__ __forceinline__ float2 normalise_point(float2 p, const Norm& nm)
     return make_float2(__fmul_rn(__fsub_rn(p.x, nm.cx), nm.scale), __fmul_rn(__fsub_rn(p.y, nm.cy), nm.scale));
 }
 
-// column c (0..8) of the design-matrix row of one match, float32 products like the reference
-__device__ __forceinline__ float design_elem(float2 a, float2 b, int c)
-{
-    switch (c) {
-    case 0: return __fmul_rn(a.x, b.x);
-    case 1: return __fmul_rn(a.y, b.x);
-    case 2: return b.x;
-    case 3: return __fmul_rn(a.x, b.y);
-    case 4: return __fmul_rn(a.y, b.y);
-    case 5: return b.y;
-    case 6: return a.x;
-    case 7: return a.y;
-    default: return 1.0f;
-    }
-}
-
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// The shared solve of F_8Point (multiview.hpp:150-176) and of one F_Sampson iteration (:197-238):
+// the 9x9 normal matrix of the (optionally re-weighted) N x 9 design matrix on the FP64 tensor
+// cores, its null vector by Jacobi, the rank-2 projection.  s_Fw != nullptr: rows are scaled by
+// the Sampson weight computed from the float32 matrix s_Fw (and by wuser[i] if given).  Thread 0
+// returns with F (row-major, rank 2, float32-rounded like the reference's Matrix3f) -- in the
+// NORMALISED frame.  All threads must call; ends with a barrier.
+__device__ void solve_normalised(const float2* __restrict__ pa, const float2* __restrict__ pb, int n, const Norm& na,
+                                 const Norm& nb, const float* s_Fw, const float* __restrict__ wuser, double* s_G,
+                                 double* s_V, double* F)
+{
+    for (int i = threadIdx.x; i < 81; i += kF8Threads) s_G[i] = 0.0;
+    __syncthreads();
+    float Fw[9], Fwt[9];
+    if (s_Fw)
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) { Fw[r * 3 + c] = s_Fw[r * 3 + c]; Fwt[r * 3 + c] = s_Fw[c * 3 + r]; }
+
+    // 8x8 block of A^T A on the FP64 tensor cores: per MMA one warp contracts 4 matches.
+    // A-operand (8x4, row = lane/4, k = lane%4) and B-operand (4x8, k = lane%4, col = lane/4) are the
+    // same number: element `lane/4` of the design row of match `4*chunk + lane%4`.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = lane >> 2, kk = lane & 3;
+    double d0 = 0.0, d1 = 0.0, col8 = 0.0, g88 = 0.0;
+    const int nchunks = (n + 3) >> 2;
+    for (int ch = warp; ch < nchunks; ch += kF8Threads / 32) {
+        const int i = 4 * ch + kk;
+        double e = 0.0, e8 = 0.0;
+        if (i < n) {
+            const float2 a = normalise_point(pa[i], na), b = normalise_point(pb[i], nb);
+            float w = 1.0f;
+            if (s_Fw) {     // W = 1 / (L.x^2 + L.y^2 + R.x^2 + R.y^2), L = eline(F^T, pB), R = eline(F, pA)  (:199-203)
+                const float lx = __fadd_rn(__fadd_rn(__fmul_rn(Fwt[0], b.x), __fmul_rn(Fwt[1], b.y)), Fwt[2]);
+                const float ly = __fadd_rn(__fadd_rn(__fmul_rn(Fwt[3], b.x), __fmul_rn(Fwt[4], b.y)), Fwt[5]);
+                const float lz = __fadd_rn(__fadd_rn(__fmul_rn(Fwt[6], b.x), __fmul_rn(Fwt[7], b.y)), Fwt[8]);
+                const float rx = __fadd_rn(__fadd_rn(__fmul_rn(Fw[0], a.x), __fmul_rn(Fw[1], a.y)), Fw[2]);
+                const float ry = __fadd_rn(__fadd_rn(__fmul_rn(Fw[3], a.x), __fmul_rn(Fw[4], a.y)), Fw[5]);
+                const float rz = __fadd_rn(__fadd_rn(__fmul_rn(Fw[6], a.x), __fmul_rn(Fw[7], a.y)), Fw[8]);
+                const float Lx = __fdiv_rn(lx, lz), Ly = __fdiv_rn(ly, lz), Rx = __fdiv_rn(rx, rz), Ry = __fdiv_rn(ry, rz);
+                float den = __fmul_rn(Lx, Lx);
+                den = __fadd_rn(den, __fmul_rn(Ly, Ly));
+                den = __fadd_rn(den, __fmul_rn(Rx, Rx));
+                den = __fadd_rn(den, __fmul_rn(Ry, Ry));
+                w = __fdiv_rn(1.0f, den);
+                if (wuser) w = __fmul_rn(wuser[i], w);
+            }
+            // row elements as the reference forms them: ((w * first) * second), float32
+            float el;
+            switch (col) {
+            case 0: el = s_Fw ? __fmul_rn(__fmul_rn(w, a.x), b.x) : __fmul_rn(a.x, b.x); break;
+            case 1: el = s_Fw ? __fmul_rn(__fmul_rn(w, a.y), b.x) : __fmul_rn(a.y, b.x); break;
+            case 2: el = s_Fw ? __fmul_rn(w, b.x) : b.x; break;
+            case 3: el = s_Fw ? __fmul_rn(__fmul_rn(w, a.x), b.y) : __fmul_rn(a.x, b.y); break;
+            case 4: el = s_Fw ? __fmul_rn(__fmul_rn(w, a.y), b.y) : __fmul_rn(a.y, b.y); break;
+            case 5: el = s_Fw ? __fmul_rn(w, b.y) : b.y; break;
+            case 6: el = s_Fw ? __fmul_rn(w, a.x) : a.x; break;
+            default: el = s_Fw ? __fmul_rn(w, a.y) : a.y; break;
+            }
+            e = (double)el;
+            e8 = (double)w;                                   // ninth column: w * 1
+        }
+        col8 += e * e8;
+        if (col == 0) g88 += e8 * e8;
+        dmma_m8n8k4(d0, d1, e, e);
+    }
+    // accumulator fragment: row = lane/4, columns 2*(lane%4) and +1
+    atomicAdd(&s_G[col * 9 + 2 * kk], d0);
+    atomicAdd(&s_G[col * 9 + 2 * kk + 1], d1);
+    // ninth row / column
+    col8 += __shfl_xor_sync(0xffffffffu, col8, 1);
+    col8 += __shfl_xor_sync(0xffffffffu, col8, 2);
+    g88 += __shfl_xor_sync(0xffffffffu, g88, 1);
+    g88 += __shfl_xor_sync(0xffffffffu, g88, 2);
+    if (kk == 0) { atomicAdd(&s_G[col * 9 + 8], col8); atomicAdd(&s_G[8 * 9 + col], col8); }
+    if (lane == 0) atomicAdd(&s_G[80], g88);
+    __syncthreads();
+
+    if (threadIdx.x == 0) {
+        tpose::sm::jacobi_eigen<9>(s_G, s_V);
+        const int m = tpose::sm::argmin_diag<9>(s_G);
+        for (int i = 0; i < 9; i++) F[i] = (double)(float)s_V[i * 9 + m];      // VectorXf f -> Matrix3f F
+        tpose::sm::rank2_project(F);
+        for (int i = 0; i < 9; i++) F[i] = (double)(float)F[i];                // held as Matrix3f
+    }
+    __syncthreads();
+}
+
+// F = HB^T F HA, then / F(2,2); H = [[s,0,-cx s],[0,s,-cy s],[0,0,1]] with float32 entries (multiview.hpp:80-84,178-179)
+__device__ void denormalise(const double* F, const Norm& na, const Norm& nb, double* R)
+{
+    const double HA[9] = {na.scale, 0, (double)__fmul_rn(-na.cx, na.scale), 0, na.scale, (double)__fmul_rn(-na.cy, na.scale), 0, 0, 1};
+    const double HB[9] = {nb.scale, 0, (double)__fmul_rn(-nb.cx, nb.scale), 0, nb.scale, (double)__fmul_rn(-nb.cy, nb.scale), 0, 0, 1};
+    double T[9];
+    tpose::sm::mat3_tmul(HB, F, T);
+    tpose::sm::mat3_mul(T, HA, R);
+    const double s = R[8];
+    for (int i = 0; i < 9; i++) R[i] /= s;
+}
+
 // offsets[nb+1]: match range of each pair inside A / B.  F9: nb x 9 floats, row-major.
+// iters == 0: F_8Point (multiview.hpp:130-183).  iters > 0: F_Sampson (:187-299), i.e. the 8-point
+// result, then `iters` solves re-weighted by the Sampson denominators of the current F; wuser
+// (may be null) are the per-match weights of the three-argument overload.  The first iteration
+// uses the DE-normalised 8-point F with the normalised points, like the reference (:189-205).
 __global__ void __launch_bounds__(kF8Threads)
-k_f8point(const float2* __restrict__ A, const float2* __restrict__ B, const int* __restrict__ offsets, float* __restrict__ F9)
+k_f8point(const float2* __restrict__ A, const float2* __restrict__ B, const int* __restrict__ offsets,
+          const float* __restrict__ wuser, int iters, float* __restrict__ F9)
 {
     __shared__ double s_red[kF8Threads / 32];
     __shared__ double s_G[81];                 // A^T A
     __shared__ double s_V[81];
+    __shared__ float s_F[9];
     const int pair = blockIdx.x;
     const int o0 = offsets[pair], n = offsets[pair + 1] - o0;
     float* out = F9 + 9 * pair;
@@ -104,46 +192,22 @@ k_f8point(const float2* __restrict__ A, const float2* __restrict__ B, const int*
     const float2* pb = B + o0;
     const Norm na = normalise_stats(pa, n, s_red);
     const Norm nb = normalise_stats(pb, n, s_red);
-    for (int i = threadIdx.x; i < 81; i += kF8Threads) s_G[i] = 0.0;
-    __syncthreads();
-
-    // 8x8 block of A^T A on the FP64 tensor cores: per MMA one warp contracts 4 matches.
-    // A-operand (8x4, row = lane/4, k = lane%4) and B-operand (4x8, k = lane%4, col = lane/4) are the
-    // same number: element `lane/4` of the design row of match `4*chunk + lane%4`.
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int col = lane >> 2, kk = lane & 3;
-    double d0 = 0.0, d1 = 0.0, colsum = 0.0;
-    const int nchunks = (n + 3) >> 2;
-    for (int ch = warp; ch < nchunks; ch += kF8Threads / 32) {
-        const int i = 4 * ch + kk;
-        double e = 0.0;
-        if (i < n) e = (double)design_elem(normalise_point(pa[i], na), normalise_point(pb[i], nb), col);
-        colsum += e;
-        dmma_m8n8k4(d0, d1, e, e);
+    double F[9], R[9];
+    solve_normalised(pa, pb, n, na, nb, nullptr, nullptr, s_G, s_V, F);
+    if (threadIdx.x == 0) {
+        denormalise(F, na, nb, R);
+        for (int i = 0; i < 9; i++) s_F[i] = (float)R[i];
     }
-    // accumulator fragment: row = lane/4, columns 2*(lane%4) and +1
-    atomicAdd(&s_G[col * 9 + 2 * kk], d0);
-    atomicAdd(&s_G[col * 9 + 2 * kk + 1], d1);
-    // ninth row / column: the design matrix's last column is all ones, so it is the column sums
-    colsum += __shfl_xor_sync(0xffffffffu, colsum, 1);
-    colsum += __shfl_xor_sync(0xffffffffu, colsum, 2);
-    if (kk == 0) { atomicAdd(&s_G[col * 9 + 8], colsum); atomicAdd(&s_G[8 * 9 + col], colsum); }
-    if (threadIdx.x == 0) s_G[80] = (double)n;
     __syncthreads();
-
-    if (threadIdx.x != 0) return;
-    tpose::sm::jacobi_eigen<9>(s_G, s_V);
-    const int m = tpose::sm::argmin_diag<9>(s_G);
-    double F[9];
-    for (int i = 0; i < 9; i++) F[i] = (double)(float)s_V[i * 9 + m];      // VectorXf f -> Matrix3f F
-    tpose::sm::rank2_project(F);
-    // F = HB^T F HA; H = [[s,0,-cx s],[0,s,-cy s],[0,0,1]] with float32 entries (multiview.hpp:80-84)
-    const double HA[9] = {na.scale, 0, (double)__fmul_rn(-na.cx, na.scale), 0, na.scale, (double)__fmul_rn(-na.cy, na.scale), 0, 0, 1};
-    const double HB[9] = {nb.scale, 0, (double)__fmul_rn(-nb.cx, nb.scale), 0, nb.scale, (double)__fmul_rn(-nb.cy, nb.scale), 0, 0, 1};
-    double T[9], R[9];
-    tpose::sm::mat3_tmul(HB, F, T);
-    tpose::sm::mat3_mul(T, HA, R);
-    for (int i = 0; i < 9; i++) out[i] = (float)(R[i] / R[8]);
+    for (int k = 0; k < iters; k++) {
+        solve_normalised(pa, pb, n, na, nb, s_F, wuser ? wuser + o0 : nullptr, s_G, s_V, F);
+        if (threadIdx.x == 0) for (int i = 0; i < 9; i++) s_F[i] = (float)F[i];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (iters > 0) { denormalise(F, na, nb, R); for (int i = 0; i < 9; i++) out[i] = (float)R[i]; }
+        else for (int i = 0; i < 9; i++) out[i] = s_F[i];
+    }
 }
 
 // One thread per match of one pair (blockIdx.y = pair).  F9 / K9: per pair, row-major float.

@@ -202,6 +202,12 @@ void tph_f8point(const float* A, int na, const float* B, int nb, float* F9)
     auto F = tpose::mview::F_8Point(vec2s(A, na), vec2s(B, nb));
     std::memcpy(F9, F.m, sizeof F.m);
 }
+void tph_fsampson(const float* A, int na, const float* B, int nb, const float* w, float* F9)
+{
+    auto F = w ? tpose::mview::F_Sampson(vec2s(A, na), vec2s(B, nb), std::vector<float>(w, w + na))
+               : tpose::mview::F_Sampson(vec2s(A, na), vec2s(B, nb));
+    std::memcpy(F9, F.m, sizeof F.m);
+}
 void tph_triangulate_points(const float* F9, const float* K9, const float* A, const float* B, int n, float* X4)
 {
     tpose::mview::Matrix3f F, K;

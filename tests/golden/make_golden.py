@@ -9,6 +9,7 @@ Contents: A, B  float32 (174,2)   the matches as the reference feeds them to mul
           K     float32 (3,3)     mview::Camera()
           X, Ac, Bc               oracle triangulate(F,K,A,B) and the corrected matches
           X_nc                    the same without the optimal correction
+          F_sampson float64 (3,3) oracle/mview_oracle.f_sampson(A, B) (100 iterations)
 """
 import os
 import sys
@@ -34,7 +35,8 @@ def main():
         Ac[i], Bc[i] = M.correct_match(Ff, Ac[i], Bc[i])
     X = M.triangulate(Ff, K, A, B)
     Xnc = M.triangulate(Ff, K, A, B, correct=False)
-    np.savez(os.path.join(HERE, "sfm_matches.npz"), A=A, B=B, F=F, F_cv=Fcv, K=K, X=X, X_nc=Xnc, Ac=Ac, Bc=Bc)
+    Fs = M.f_sampson(A, B)
+    np.savez(os.path.join(HERE, "sfm_matches.npz"), A=A, B=B, F=F, F_cv=Fcv, K=K, X=X, X_nc=Xnc, Ac=Ac, Bc=Bc, F_sampson=Fs)
     print("max |F - F_cv| =", np.abs(F - Fcv).max())
 
 

@@ -152,3 +152,17 @@ def test_realroots_sorted_matches_oracle(L):
         ref = M.realroots(a7)
         assert n == len(ref)
         assert np.allclose(out[:n], ref, rtol=1e-8, atol=1e-10)
+
+
+def test_sampson_oracle_golden_and_properties(gold):
+    """oracle f_sampson (multiview.hpp:187-299): reproduces the committed fixture, is a fixed point
+    of its own iteration up to float32 noise, and unit weights are a no-op.  (The reference's
+    weighting -- W, not sqrt(W), of lines divided by their z -- does not lower the textbook Sampson
+    cost on its own match list; it is restated as it is.)"""
+    A, B = gold["A"], gold["B"]
+    F = M.f_sampson(A, B)
+    assert np.abs(F - gold["F_sampson"]).max() <= 1e-12 * np.abs(F).max()
+    F101 = M.f_sampson(A, B, iters=101)
+    assert np.abs(F101 - F).max() < 1e-4 * np.abs(F).max()
+    assert np.abs(M.f_sampson(A, B, w=np.ones(len(A), np.float32)) - F).max() == 0.0
+

@@ -52,6 +52,43 @@ def test_f8point_golden_and_batched(cuda_pkg):
     assert np.array_equal(solo, F[3])
 
 
+def test_fsampson_golden_batched_weighted(cuda_pkg):
+    """mview::F_Sampson (multiview.hpp:187-299).  The iteration re-derives float32 weights from a
+    float32 F a hundred times; between two consecutive iterations of the oracle itself F/F(2,2)
+    moves by ~2e-5, so the bound here is 5e-4 (written down in DESIGN.md section 7)."""
+    g = np.load(GOLD)
+    rng = np.random.default_rng(1)
+    As, Bs = [g["A"]], [g["B"]]
+    for n in (12, 200, 1581):
+        a, b = _synthetic_pair(rng, n, 2e-3)
+        As.append(a); Bs.append(b)
+    F = cuda_pkg.fsampson(As, Bs)
+    assert _close(F[0], g["F_sampson"], 5e-4), np.abs(F[0] - g["F_sampson"]).max() / np.abs(g["F_sampson"]).max()
+    for i in range(1, len(As)):
+        ref = M.f_sampson(As[i], Bs[i])
+        assert _close(F[i], ref, 5e-4), (i, np.abs(F[i] - ref).max() / np.abs(ref).max())
+    # zero iterations is F_8Point
+    assert np.array_equal(cuda_pkg.fsampson(As, Bs, iterations=0), cuda_pkg.f8point(As, Bs))
+    # unit weights change nothing; real weights follow the three-argument overload
+    ones = [np.ones(len(a), np.float32) for a in As]
+    assert np.array_equal(cuda_pkg.fsampson(As, Bs, weights=ones), F)
+    w = [rng.uniform(0.2, 1.0, len(a)).astype(np.float32) for a in As]
+    Fw = cuda_pkg.fsampson(As, Bs, weights=w)
+    for i in (0, 2):
+        ref = M.f_sampson(As[i], Bs[i], w=w[i])
+        assert _close(Fw[i], ref, 5e-4), (i, np.abs(Fw[i] - ref).max() / np.abs(ref).max())
+    # empty list -> identity, like F_8Point
+    Fe = cuda_pkg.fsampson([np.zeros((0, 2), np.float32)], [np.zeros((0, 2), np.float32)])
+    assert np.array_equal(Fe[0], np.eye(3, dtype=np.float32))
+    # the C++ header drives the same kernel
+    L = H.ours()
+    F9 = np.zeros(9, np.float32)
+    L.f("fsampson")(H._p(g["A"]), len(g["A"]), H._p(g["B"]), len(g["B"]), None, H._p(F9))
+    assert np.array_equal(F9.reshape(3, 3), F[0])
+    L.f("fsampson")(H._p(g["A"]), len(g["A"]), H._p(g["B"]), len(g["B"]), H._p(w[0]), H._p(F9))
+    assert np.array_equal(F9.reshape(3, 3), Fw[0])
+
+
 def test_triangulate_golden(cuda_pkg):
     g = np.load(GOLD)
     F = g["F"].astype(np.float32)
