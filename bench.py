@@ -127,6 +127,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     pkg = entry.load_package()
     synth = importlib.import_module("tpose_b200.synth")
     O = entry.load_oracle()

@@ -746,6 +746,7 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
         rc = rebuild_edges(ctxs[i]);
         if (rc) { if (ctxs[i] != lead) lead->err = "batch: job " + std::to_string(i) + ": " + ctxs[i]->err; return rc; }
         jobs[(size_t)i] = make_job(ctxs[i], slot, flavour);
+        jobs[(size_t)i].flip = ctxs[i]->cur ^ lead->cur;   // contexts need not have done the same number of steps
         mxp = ctxs[i]->NP > mxp ? ctxs[i]->NP : mxp;
         mxe = ctxs[i]->NE > mxe ? ctxs[i]->NE : mxe;
         narrow = narrow && narrow_sums(ctxs[i]->img[slot].W, ctxs[i]->img[slot].H);
@@ -769,15 +770,11 @@ extern "C" int tpose_cuda_batch_step(tpose_cuda_ctx* const* ctxs, int n, const i
     if (rc) return rc;
     tpose_cuda_ctx* ctx = ctxs[0];
     if (nsteps < 0) return fail(ctx, TPOSE_ERR_ARG, "batch_step: nsteps < 0");
-    // all jobs must write the same set parity: bring every context to the leader's
-    for (int i = 1; i < n; i++)
-        if (ctxs[i]->cur != ctx->cur) return fail(ctx, TPOSE_ERR_STATE, "batch: contexts are out of step (mix of stepped and fresh contexts)");
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     rc = issue_steps(ctx, ctx->batch_jobs, n, shape, fused_flags(flavour), ctx->cur ^ 1, nsteps);
     if (rc) return rc;
-    const int cur = (ctx->cur + nsteps) & 1;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    for (int i = 0; i < n; i++) ctxs[i]->cur = cur;
+    for (int i = 0; i < n; i++) ctxs[i]->cur = (ctxs[i]->cur + nsteps) & 1;
     return TPOSE_OK;
 }
 
@@ -789,8 +786,6 @@ extern "C" int tpose_cuda_batch_run(tpose_cuda_ctx* const* ctxs, int n, const in
     if (rc) return rc;
     tpose_cuda_ctx* ctx = ctxs[0];
     if (max_steps < 1) return fail(ctx, TPOSE_ERR_ARG, "batch_run: max_steps < 1");
-    for (int i = 1; i < n; i++)
-        if (ctxs[i]->cur != ctx->cur) return fail(ctx, TPOSE_ERR_STATE, "batch: contexts are out of step");
     for (int i = 0; i < n; i++) CK(cudaMemsetAsync(ctxs[i]->run_state, 0, sizeof(int) * 4, ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     const int first = ctx->cur ^ 1;
@@ -803,7 +798,7 @@ extern "C" int tpose_cuda_batch_run(tpose_cuda_ctx* const* ctxs, int n, const in
     CK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < n; i++) {
         const int done = rs[(size_t)4 * i + RS_STEPS];
-        if (done > 0) ctxs[i]->cur = (first + done - 1) & 1;
+        if (done > 0) ctxs[i]->cur = ((ctxs[i]->cur ^ 1) + done - 1) & 1;
         if (steps_done) steps_done[i] = done;
         if (trigger_flags) trigger_flags[i] = (uint32_t)rs[(size_t)4 * i + RS_TRIG];
     }

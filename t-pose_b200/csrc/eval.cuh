@@ -62,6 +62,7 @@ struct EvalJob {
     float2* pts;
     const int4* tri;
     int NT, NP, NE;
+    int flip;                  // 1: this job's buffer sets are swapped relative to the launch's `set` argument
     float ratio, dp, step;
     int* cn[2]; int4* ca[2]; int* ten[2];   // two buffer sets, alternating per step
     int2* gr;                  // pgradbuf as the reference sees it (written by the vertex update)
@@ -232,6 +233,7 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
         reinterpret_cast<int*>(&J)[tid] = reinterpret_cast<const int*>(jobs + blockIdx.y)[tid];
     __syncthreads();
     if ((flags & EV_HONOUR_STOP) && __ldcg(&J.run_state[RS_STOP])) return;
+    set ^= J.flip;
 
     if (blockIdx.x == gridDim.x - 1) {
         // service block: the previous frame's host-side checks
@@ -364,6 +366,7 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags)
     // RS_STOP is raised by this kernel's first block only when this very launch decided to stop;
     // a block that sees it then skips work that is discarded anyway
     if ((flags & EV_HONOUR_STOP) && __ldcg(&J.run_state[RS_STOP])) return;
+    set ^= J.flip;
     int* const cn = J.cn[set]; int4* const ca = J.ca[set]; int* const ten = J.ten[set];
 
     const int nvb = (int)gridDim.x - kBaseBlocks;           // blocks that take vertices

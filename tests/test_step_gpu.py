@@ -289,7 +289,10 @@ def test_batch_equals_individual_contexts(cuda_pkg, synth, O):
         c = _ctx(cuda_pkg)
         c.set_image(0, img); c.upload(pts, tri, ratio)
         ctxs.append(c)
-    cuda_pkg.batch_step(ctxs, cuda_pkg.TRIANGULATE, 4)
+    # contexts need not have done the same number of steps before they join a batch
+    ctxs[1].step(0, cuda_pkg.TRIANGULATE, 1)
+    cuda_pkg.batch_step(ctxs, cuda_pkg.TRIANGULATE, 3)
+    cuda_pkg.batch_step([ctxs[0], ctxs[2]], cuda_pkg.TRIANGULATE, 1)
     for c, s in zip(ctxs, solo):
         got = c.retrieve()
         for k in ("cn", "ca", "ten"):
