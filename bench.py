@@ -209,15 +209,21 @@ def run_ours(args):
     barrier()
     t_wall0 = time.perf_counter()
     ms_cold = 0.0
-    ms_edges = 0.0
     for _ in range(K):
         ctx.flush_l2(L2_FLUSH_BYTES)          # not inside the event bracket of the step
-        ctx.step(0, pkg.TRIANGULATE, 1)       # ev0 . k_edges . ev_mid . k_corners . ev1 on the context's stream
+        ctx.step(0, pkg.TRIANGULATE, 1)       # ev0 . k_edges . k_corners . ev1 on the context's stream
         ms_cold += ctx.last_elapsed_ms()
-        ms_edges += ctx.last_kernel_ms()[0]
     barrier()
     launches = ctx.launch_count() - launches0
     ms_cold = max_over_ranks(ms_cold)
+    # the dominant kernel alone (an event between the two kernels; not part of the timed K steps)
+    ctx.set_kernel_timing(True)
+    ms_edges, Kk = 0.0, min(K, 100)
+    for _ in range(Kk):
+        ctx.flush_l2(L2_FLUSH_BYTES)
+        ctx.step(0, pkg.TRIANGULATE, 1)
+        ms_edges += ctx.last_kernel_ms()[0]
+    ctx.set_kernel_timing(False)
     # ---- same K steps without the flush: the optimiser's steady state (table stays in L2).
     # One untimed pass first, so that the graphs the K steps replay are already instantiated.
     ctx.upload(pts, tri, ratio)
@@ -282,7 +288,7 @@ def run_ours(args):
         balg = b_alg(w, h, NT, NP)
         cold_s = ms_cold / 1000.0
         warm_s = ms_warm / 1000.0
-        edges_s = ms_edges / 1000.0 / K          # mean duration of one k_edges launch (cold)
+        edges_s = ms_edges / 1000.0 / Kk         # mean duration of one k_edges launch (cold)
         achieved = balg / edges_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")

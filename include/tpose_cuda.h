@@ -184,9 +184,10 @@ int tpose_cuda_raster_ids(tpose_cuda_ctx *ctx, int slot, int32_t *ids_host);
 /* Device time in milliseconds of the most recent step/run call on this
  * context, measured with CUDA events on the context's stream. */
 int tpose_cuda_last_elapsed_ms(tpose_cuda_ctx *ctx, float *ms);
-/* Device time of the two kernels of the most recent tpose_cuda_step(.., nsteps = 1): the edge
- * integrals (k_edges) and the per-variant evaluation + vertex update (k_corners).
- * TPOSE_ERR_STATE after any other kind of call. */
+/* Per-kernel timing (off by default: it puts an event between the two kernels of a step).  When on, tpose_cuda_last_kernel_ms gives the device time of the two
+ * kernels of the most recent tpose_cuda_step(.., nsteps = 1): the edge integrals (k_edges) and the
+ * per-variant evaluation + vertex update (k_corners).  TPOSE_ERR_STATE after any other call. */
+int tpose_cuda_set_kernel_timing(tpose_cuda_ctx *ctx, int on);
 int tpose_cuda_last_kernel_ms(tpose_cuda_ctx *ctx, float *edges_ms, float *corners_ms);
 /* Block until the context's stream is idle. */
 int tpose_cuda_sync(tpose_cuda_ctx *ctx);

@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtpose_cuda.so")
+LIB_PATH = os.environ.get("TPOSE_CUDA_LIB") or os.path.join(_HERE, "libtpose_cuda.so")   # override: development experiments
 
 TRIANGULATE, WARP = 0, 1
 IMAGE_A, IMAGE_B = 0, 1
@@ -41,7 +41,7 @@ EXPORTS = [
     "tpose_cuda_upload_points", "tpose_cuda_colors", "tpose_cuda_energy", "tpose_cuda_shift",
     "tpose_cuda_step", "tpose_cuda_run", "tpose_cuda_set_toterr", "tpose_cuda_get_toterr",
     "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
-    "tpose_cuda_raster_ids", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_sync",
+    "tpose_cuda_raster_ids", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_set_kernel_timing", "tpose_cuda_sync",
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
     "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
     "tpose_cuda_mview_last_ms",
@@ -208,6 +208,9 @@ class Context:
         ms = C.c_float()
         self._ck(lib().tpose_cuda_last_elapsed_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def set_kernel_timing(self, on):
+        self._ck(lib().tpose_cuda_set_kernel_timing(self._h, C.c_int(1 if on else 0)))
 
     def last_kernel_ms(self):
         """(k_edges ms, k_corners ms) of the most recent step(.., 1)."""

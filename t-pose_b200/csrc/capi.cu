@@ -71,7 +71,7 @@ struct tpose_cuda_ctx {
     int64_t launches = 0;
     int group = 0;                    // lanes per edge (0 = pick from NT and H)
     std::vector<SeqGraph> graphs; uint64_t graph_clock = 0; bool use_graphs = true;
-    bool mid_valid = false;
+    bool mid_valid = false, time_kernels = false;
     std::string err;
 };
 
@@ -393,18 +393,31 @@ static int rebuild_edges(tpose_cuda_ctx* ctx)
 
 static bool valid_group(int g) { return g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32; }
 
-// lanes per (edge, move) item: the mean vertical extent of an edge is about 0.6*H*sqrt(2/NT) rows
-static int group_for_rows(double rows)
+// Lanes per (edge, move) item.  More lanes shorten the serial row walk of an item (what a single
+// image needs: it cannot fill the machine anyway) but repeat its set-up (two snaps, two integer
+// divisions) per lane (what a batch pays for).  So: as many lanes as it takes to put ~250 k lanes
+// on the device, but at least 4 rows per lane.  The mean vertical extent of an edge is about
+// 0.6*H*sqrt(2/NT) rows.
+static int pow2_floor(double x)
 {
     int g = 1;
-    while (g < 32 && rows / g > 12.0) g <<= 1;
+    while (g < 32 && 2.0 * g <= x) g <<= 1;
     return g;
 }
+
+static int group_for(double mean_rows, double total_items)
+{
+    const int fill = pow2_floor(250000.0 / (total_items > 1.0 ? total_items : 1.0));
+    const int rows = pow2_floor(mean_rows / 4.0);
+    return fill < rows ? fill : rows;
+}
+
+static double mean_edge_rows(int NT, int H) { return 0.6 * (double)H * sqrt(2.0 / (double)NT); }
 
 static int pick_group(const tpose_cuda_ctx* ctx, int NT, int H)
 {
     if (valid_group(ctx->group)) return ctx->group;
-    return group_for_rows(0.6 * (double)H * sqrt(2.0 / (double)NT));
+    return group_for(mean_edge_rows(NT, H), (double)ctx->NE * kEdgeMoves);
 }
 
 // 32-bit colour sums are exact while 255*W*H < 2^31
@@ -484,8 +497,9 @@ static int issue_sequence(tpose_cuda_ctx* ctx, const SeqKey& key)
 {
     ctx->launches += (int64_t)kLaunchesPerEval * key.len;
     if (key.len < kGraphMinLen || !ctx->use_graphs) {
-        issue_direct(key, ctx->stream, key.len == 1 ? ctx->ev_mid : nullptr);
-        ctx->mid_valid = key.len == 1;
+        const bool mid = key.len == 1 && ctx->time_kernels;
+        issue_direct(key, ctx->stream, mid ? ctx->ev_mid : nullptr);
+        ctx->mid_valid = mid;
         CK(cudaGetLastError());
         return TPOSE_OK;
     }
@@ -735,7 +749,7 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
     tpose_cuda_ctx* lead = ctxs[0];
     tpose_cuda_ctx* ctx = lead;   // for CK
     std::vector<EvalJob> jobs((size_t)n);
-    int mxp = 0, mxe = 0; double rows = 0.0; bool narrow = true;
+    int mxp = 0, mxe = 0; double rows = 0.0, items = 0.0; bool narrow = true;
     for (int i = 0; i < n; i++) {
         const int slot = slots ? slots[i] : 0;
         int rc = check_ready(ctxs[i], slot, flavour);
@@ -749,8 +763,9 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
         jobs[(size_t)i].flip = ctxs[i]->cur ^ lead->cur;   // contexts need not have done the same number of steps
         mxp = ctxs[i]->NP > mxp ? ctxs[i]->NP : mxp;
         mxe = ctxs[i]->NE > mxe ? ctxs[i]->NE : mxe;
+        items += (double)ctxs[i]->NE * kEdgeMoves;
         narrow = narrow && narrow_sums(ctxs[i]->img[slot].W, ctxs[i]->img[slot].H);
-        rows += 0.6 * ctxs[i]->img[slot].H * sqrt(2.0 / ctxs[i]->NT);
+        rows += mean_edge_rows(ctxs[i]->NT, ctxs[i]->img[slot].H);
     }
     if (lead->batch_cap < n) {
         cudaFree(lead->batch_jobs); lead->batch_jobs = nullptr; lead->batch_cap = 0;
@@ -759,7 +774,7 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
     }
     CK(cudaMemcpyAsync(lead->batch_jobs, jobs.data(), sizeof(EvalJob) * n, cudaMemcpyHostToDevice, lead->stream));
     CK(cudaStreamSynchronize(lead->stream));   // `jobs` is a local
-    *shape = make_shape(valid_group(lead->group) ? lead->group : group_for_rows(rows / n), mxp, mxe, narrow);
+    *shape = make_shape(valid_group(lead->group) ? lead->group : group_for(rows / n, items), mxp, mxe, narrow);
     return TPOSE_OK;
 }
 
@@ -926,16 +941,39 @@ extern "C" int tpose_cuda_last_elapsed_ms(tpose_cuda_ctx* ctx, float* ms)
     return TPOSE_OK;
 }
 
+extern "C" int tpose_cuda_set_kernel_timing(tpose_cuda_ctx* ctx, int on)
+{
+    if (!ctx) return TPOSE_ERR_ARG;
+    ctx->time_kernels = on != 0;
+    return TPOSE_OK;
+}
+
 extern "C" int tpose_cuda_last_kernel_ms(tpose_cuda_ctx* ctx, float* edges_ms, float* corners_ms)
 {
     if (!ctx || !edges_ms || !corners_ms) return TPOSE_ERR_ARG;
-    if (!ctx->mid_valid) return fail(ctx, TPOSE_ERR_STATE, "last_kernel_ms: the last call was not a single tpose_cuda_step(.., 1)");
+    if (!ctx->mid_valid) return fail(ctx, TPOSE_ERR_STATE, "last_kernel_ms: needs tpose_cuda_set_kernel_timing(ctx, 1) and a single tpose_cuda_step(.., 1) as the last call");
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventSynchronize(ctx->ev1));
     CK(cudaEventElapsedTime(edges_ms, ctx->ev0, ctx->ev_mid));
     CK(cudaEventElapsedTime(corners_ms, ctx->ev_mid, ctx->ev1));
     return TPOSE_OK;
 }
+
+#ifdef TPOSE_TIMELINE
+// development aid: out[2][6][8192] globaltimer stamps (ns) per warp; reset != 0 zeroes them
+extern "C" int tpose_cuda_debug_timeline(unsigned long long* out, int reset)
+{
+    cudaDeviceSynchronize();
+    if (out) cudaMemcpyFromSymbol(out, g_timeline, sizeof(unsigned long long) * 2 * 6 * kTlWarps);
+    if (reset) {
+        void* p = nullptr;
+        cudaGetSymbolAddress(&p, g_timeline);
+        cudaMemset(p, 0, sizeof(unsigned long long) * 2 * 6 * kTlWarps);
+        cudaDeviceSynchronize();
+    }
+    return 0;
+}
+#endif
 
 extern "C" int tpose_cuda_sync(tpose_cuda_ctx* ctx)
 {

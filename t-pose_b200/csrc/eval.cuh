@@ -182,44 +182,74 @@ __device__ void geterr_serial(const int* __restrict__ ten_base, int nt, float* s
 
 constexpr int kEdgeThreads = 256;
 
+// Development aid (-DTPOSE_TIMELINE): first / last globaltimer stamp over all threads at a few
+// points of the two kernels, read back with tpose_cuda_debug_timeline.
+#ifdef TPOSE_TIMELINE
+constexpr int kTlWarps = 8192;
+__device__ unsigned long long g_timeline[2][6][kTlWarps];
+__device__ __forceinline__ void tl_mark(int kernel, int phase)
+{
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        if (w < kTlWarps) g_timeline[kernel][phase][w] = t;
+    }
+}
+#define TL(k, p) tl_mark(k, p)
+#else
+#define TL(k, p)
+#endif
+
 template <typename T> __device__ __forceinline__ T shfl_xor_any(T v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
 
 // Walks the rows of one edge (this lane's share: rows r, r+G, ...) and sums the table entries at
 // the crossings.  ACC is the accumulator type of the three colour sums: 32 bits are enough when
 // 255*W*H < 2^31 (every image up to 3840x2160), else 64.
+// Rows are taken kWalkBatch at a time: all loads of a batch are issued (predicated off past the
+// end of the edge) before the first one is consumed, so a lane pays one memory latency per batch,
+// not per row, and there is no serial remainder loop.
+#ifndef TPOSE_WALK_BATCH
+#define TPOSE_WALK_BATCH 8
+#endif
+constexpr int kWalkBatch = TPOSE_WALK_BATCH;
+
+template <int G, typename ACC, typename REM>
+__device__ __forceinline__ void walk_rows(int rr, const int r_end, int q, const int dq, REM rem, const REM den, const REM dr,
+                                          const uint4* __restrict__ table, int row, const int rstep, const int W,
+                                          unsigned& n, unsigned& odd, ACC& sr, ACC& sg, ACC& sb, unsigned long long& s2)
+{
+    for (; rr < r_end; rr += kWalkBatch * G) {
+        uint4 e[kWalkBatch];
+        int c[kWalkBatch];
+#pragma unroll
+        for (int u = 0; u < kWalkBatch; u++) {
+            const bool on = rr + u * G < r_end;
+            c[u] = on ? min(max(q, 0), W) : 0;
+            e[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (on) e[u] = __ldg(table + (row + c[u]));     // entry index: (W+1)*H <= 4096*8192 fits 32 bits
+            q += dq; rem += dr;
+            if (rem >= den) { rem -= den; ++q; }
+            row += rstep;
+        }
+#pragma unroll
+        for (int u = 0; u < kWalkBatch; u++) {
+            n += (unsigned)c[u]; odd += e[u].x >> 20; sr += (ACC)(e[u].x & 0xFFFFFu);
+            sg += (ACC)e[u].y; sb += (ACC)e[u].z; s2 += e[u].w;
+        }
+    }
+}
+
 template <int G, typename ACC>
 __device__ __forceinline__ void walk_edge(EdgeWalk& w, const uint4* __restrict__ table, int pitch, int W,
                                           unsigned& n, unsigned& odd, ACC& sr, ACC& sg, ACC& sb, unsigned long long& s2)
 {
-    int row = w.r * pitch;                     // entry index: (W+1)*H <= 4096*8192 fits 32 bits
-    const int rstep = G * pitch;
-    const int r_end = w.r_end;
-    int rr = w.r, q = w.q;
-    const int dq = w.dq;
-    if (w.den < (1ll << 30)) {                 // every on-screen edge: remainders fit 32 bits
-        int rem = (int)w.rem;
-        const int den = (int)w.den, dr = (int)w.dr;
-#pragma unroll 4
-        for (; rr < r_end; rr += G) {
-            const int c = min(max(q, 0), W);
-            const uint4 e = __ldg(table + (row + c));
-            n += (unsigned)c; odd += e.x >> 20; sr += (ACC)(e.x & 0xFFFFFu); sg += (ACC)e.y; sb += (ACC)e.z; s2 += e.w;
-            q += dq; rem += dr;
-            if (rem >= den) { rem -= den; ++q; }
-            row += rstep;
-        }
-    } else {
-        long long rem = w.rem;
-        const long long den = w.den, dr = w.dr;
-        for (; rr < r_end; rr += G) {
-            const int c = min(max(q, 0), W);
-            const uint4 e = __ldg(table + (row + c));
-            n += (unsigned)c; odd += e.x >> 20; sr += (ACC)(e.x & 0xFFFFFu); sg += (ACC)e.y; sb += (ACC)e.z; s2 += e.w;
-            q += dq; rem += dr;
-            if (rem >= den) { rem -= den; ++q; }
-            row += rstep;
-        }
-    }
+    if (w.den < (1ll << 30))                   // every on-screen edge: remainders fit 32 bits
+        walk_rows<G, ACC, int>(w.r, w.r_end, w.q, w.dq, (int)w.rem, (int)w.den, (int)w.dr, table, w.r * pitch, G * pitch, W,
+                               n, odd, sr, sg, sb, s2);
+    else
+        walk_rows<G, ACC, long long>(w.r, w.r_end, w.q, w.dq, w.rem, w.den, w.dr, table, w.r * pitch, G * pitch, W,
+                                     n, odd, sr, sg, sb, s2);
 }
 
 // G lanes per (edge, move) item.  The last block of each job's row is the service block.
@@ -229,9 +259,11 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
 {
     __shared__ EvalJob J;
     const int tid = threadIdx.x;
+    TL(0, 0);
     if (tid < (int)(sizeof(EvalJob) / sizeof(int)))
         reinterpret_cast<int*>(&J)[tid] = reinterpret_cast<const int*>(jobs + blockIdx.y)[tid];
     __syncthreads();
+    TL(0, 1);
     if ((flags & EV_HONOUR_STOP) && __ldcg(&J.run_state[RS_STOP])) return;
     set ^= J.flip;
 
@@ -263,6 +295,9 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
             const int e = item / kEdgeMoves, q = item - e * kEdgeMoves;
             const int2 ev = __ldg(J.edges + e);
             const float2 pa = J.pts[ev.x], pb = J.pts[ev.y];
+#ifdef TPOSE_TIMELINE
+            if (pa.x + pb.x != 12345.0f) TL(0, 2);
+#endif
             float dxa = 0.0f, dya = 0.0f, dxb = 0.0f, dyb = 0.0f;
             if (q >= 1 && q <= 4) fd_offset(q - 1, J.dp, dxa, dya);
             if (q >= 5) fd_offset(q - 5, J.dp, dxb, dyb);
@@ -270,7 +305,13 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
             EdgeWalk w;
             w.init(a, b, J.H, lane, G);
             sign = w.sign;
+#ifdef TPOSE_TIMELINE
+            if (w.q != 0x7fffffff) TL(0, 3);
+#endif
             walk_edge<G, ACC>(w, J.table, J.pitch, J.W, n, odd, sr, sg, sb, s2);
+#ifdef TPOSE_TIMELINE
+            if (n + s2 != 0x7fffffffffull) TL(0, 4);
+#endif
         }
 #pragma unroll
         for (int o = G >> 1; o > 0; o >>= 1) {
@@ -285,6 +326,7 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
             J.rec[item] = rec;
         }
     }
+    TL(0, 5);
 }
 
 // ---- k_corners ----------------------------------------------------------------------------------
@@ -360,9 +402,11 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags)
 {
     __shared__ EvalJob J;
     const int tid = threadIdx.x;
+    TL(1, 0);
     if (tid < (int)(sizeof(EvalJob) / sizeof(int)))
         reinterpret_cast<int*>(&J)[tid] = reinterpret_cast<const int*>(jobs + blockIdx.y)[tid];
     __syncthreads();
+    TL(1, 1);
     // RS_STOP is raised by this kernel's first block only when this very launch decided to stop;
     // a block that sees it then skips work that is discarded anyway
     if ((flags & EV_HONOUR_STOP) && __ldcg(&J.run_state[RS_STOP])) return;
@@ -374,6 +418,7 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags)
         // base variants, one thread each
         for (int t = ((int)blockIdx.x - nvb) * kCornerThreads + tid; t < J.NT; t += kBaseBlocks * kCornerThreads)
             eval_variant(J, flags, cn, ca, ten, t, 0);
+        TL(1, 2);
         return;
     }
 
@@ -412,6 +457,9 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags)
             }
         }
         if (!(flags & EV_GRAD_SHIFT)) continue;
+#ifdef TPOSE_TIMELINE
+        if (gx != 0x12345u) TL(1, 3);
+#endif
         gx = __reduce_add_sync(0xffffffffu, gx);
         gy = __reduce_add_sync(0xffffffffu, gy);
         if (lane == 0 && !stop) {
@@ -420,6 +468,7 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags)
             if (v >= 4) J.pts[v] = shift_vertex(p, (int)gx, (int)gy, J.ratio, J.step);
         }
     }
+    TL(1, 4);
 }
 
 // un-fused gradient.cs / shift.cs, for the literal doshift() entry point
