@@ -129,6 +129,13 @@ int tpose_cuda_shift(tpose_cuda_ctx *ctx, int flavour);
  * i.e. exactly what the reference reads back at main.cpp:201-204. */
 int tpose_cuda_step(tpose_cuda_ctx *ctx, int slot, int flavour, int nsteps);
 
+/* Extension (default 1 = the reference): multiplies the step constant of shift.cs:45 (5e-5
+ * triangulate, 3e-5 warp).  The integer gradient is a sum over pixels, so the reference's constant
+ * -- tuned to its 800x450 window -- takes steps that grow with the pixel count: at 1920x1080 a
+ * two-triangle mesh never settles and a loaded 1000-triangle mesh tears itself apart (DESIGN.md
+ * section 6).  (450 / raster_h)^2 restores the reference's dynamics on a larger raster. */
+int tpose_cuda_set_step_scale(tpose_cuda_ctx *ctx, float scale);
+
 /* Up to `max_steps` frames, stopping after the first one whose geterr value
  * (float32 running sum of the base energies, relative change against the
  * previous sum -- source/triangulation.hpp:653-674) is < rel_tol.  The running
@@ -149,6 +156,13 @@ int tpose_cuda_get_toterr(tpose_cuda_ctx *ctx, float *toterr);
  * so the caller runs the reference's per-frame host code only on frames where it can do
  * something.  tri_xyzw == NULL switches the watch off.  halfedges: 3*nt twins or -1. */
 int tpose_cuda_watch(tpose_cuda_ctx *ctx, const int32_t *tri_xyzw, const int32_t *halfedges, int nt);
+
+/* After a tpose_cuda_run that stopped with TPOSE_TRIG_TOPOLOGY: one bit per triangle of the watch
+ * topology (bit t&31 of word t>>5), set where the device's conservative test fired on the frame
+ * the run stopped on -- a superset of the triangles on which prune / the 0.8*pi flip / collapse can
+ * do anything at the points that frame left.  Every other triangle can be skipped by the host's
+ * per-frame loops without changing their result.  nwords >= (NT+31)/32. */
+int tpose_cuda_watch_mask(tpose_cuda_ctx *ctx, uint32_t *mask_words, int nwords);
 
 /* ---- batches of independent jobs --------------------------------------------
  * n contexts on the same device advance in lock step, one launch per frame for all of them
@@ -218,6 +232,14 @@ int tpose_cuda_triangulate(int device, const float *F9, const float *K9, const f
  * (row-major float[12]).  X4_out is NOT divided by w; sign: largest component positive. */
 int tpose_cuda_hdlt(int device, const float *PA12, const float *PB12, const float *A_xy, const float *B_xy,
                     int n, float *X4_out);
+/* triangulation::warp / reversewarp (source/triangulation.hpp:465-520): every point of pts_xy that
+ * is not on the domain boundary (|x| >= ratio or |y| >= 1) is located in the first triangle, in
+ * index order, of the embedding from_xy that strictly contains it, and replaced by the point with
+ * the same barycentric coordinates in the embedding to_xy (both nv vec2; tri_xyzw indexes them).
+ * Same arithmetic as the host path (GLM's 3x3 inverse, float32, no FMA): identical bits.
+ * No context needed; errors through tpose_cuda_mview_last_error. */
+int tpose_cuda_carry(int device, const int32_t *tri_xyzw, int nt, const float *from_xy, const float *to_xy, int nv,
+                     float *pts_xy, int npts, float ratio);
 const char *tpose_cuda_mview_last_error(void);
 /* device milliseconds of the kernel(s) of the most recent f8point / triangulate call */
 float tpose_cuda_mview_last_ms(void);

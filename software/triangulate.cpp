@@ -2,10 +2,17 @@
 // levels of the export list to "<image>.tri" (software/triangulate/main.cpp of the reference; the
 // window, the key handlers and the mode-2 display are gone, the schedule is tpose/schedule).
 //
-//   triangulate -i image.ppm [-native] [-max N] [-frames F] [-device D]
+//   triangulate -i image.ppm [-native] [-max N] [-frames F] [-device D] [-t start.tri]
 //     -native   rasterise at the image's own size instead of the reference's 1/1.5 window
 //     -max N    extend the export list beyond 1000 in steps of 500 up to N triangles
 //     -frames F stop after F optimisation steps
+//     -stepscale S|auto  (extension) scale shift.cs's step constant; auto = (450/raster_h)^2
+//     -t file   (extension) start from the finest level of an existing .tri stack instead of the
+//               two-triangle mesh, and export only levels finer than it.  The reference's step
+//               constant (shift.cs:45) is tuned to its 800x450 window: on larger rasters the
+//               descent over a handful of huge triangles does not settle, so a
+//               large image is started from a stack grown on a reduced copy of itself -- mesh
+//               coordinates are resolution-independent.
 #include <tpose/tpose>
 #include <tpose/triangulation>
 #include <tpose/io>
@@ -33,8 +40,17 @@ int main(int argc, char* args[])
 
     tpose::init(atoi(option(argc, args, "device", "0").c_str()));               // main.cpp:78
     tpose::texture(TPOSE_IMAGE_A, img.rgba.data(), img.w, img.h, rw, rh);        // main.cpp:74
+    const std::string ss = option(argc, args, "stepscale");                      // extension, see tpose_cuda_set_step_scale
+    if (!ss.empty()) tpose::check(tpose_cuda_set_step_scale(tpose::context, ss == "auto" ? (450.0f / rh) * (450.0f / rh) : (float)atof(ss.c_str())), "stepscale");
 
     tpose::triangulation tr;                                                     // main.cpp:105-106
+    const std::string start = option(argc, args, "t");
+    if (!start.empty()) {
+        const float ratio = tpose::RATIO;
+        while (tpose::io::read(&tr, start)) {}                                   // the last record read stays in tr
+        tpose::RATIO = ratio;                                                    // io::read overwrote it (io.hpp:81)
+        while (!exportlist.empty() && exportlist.back() <= tr.NT) exportlist.pop_back();
+    }
     tpose::upload(&tr, false);
     std::cout << "Number of Triangles: " << tr.NT << std::endl;
     tpose::computecolors();                                                      // main.cpp:176
@@ -43,7 +59,8 @@ int main(int argc, char* args[])
     const auto rep = tpose::schedule::triangulate(tr, exportlist, path + ".tri", frames);
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::cout << "frames " << rep.frames << " (host body on " << rep.host_frames << "), splits " << rep.splits
-              << ", exports " << rep.exports << ", " << tr.NT << " triangles, " << sec << " s, "
+              << ", flips " << rep.flips << ", prunes " << rep.prunes << ", collapses " << rep.collapses << ", idle host frames "
+              << rep.idle_host_frames << ", exports " << rep.exports << ", " << tr.NT << " triangles, " << sec << " s, "
               << rep.frames / sec << " steps/s" << std::endl;
 
     tpose::quit();

@@ -31,6 +31,8 @@ int main(int argc, char* args[])
     tpose::init(atoi(option(argc, args, "device", "0").c_str()));
     tpose::texture(TPOSE_IMAGE_A, A.rgba.data(), A.w, A.h, rw, rh);              // warp/main.cpp:118-119
     tpose::texture(TPOSE_IMAGE_B, B.rgba.data(), B.w, B.h, rw, rh);
+    const std::string ss = option(argc, args, "stepscale");                      // extension, see tpose_cuda_set_step_scale
+    if (!ss.empty()) tpose::check(tpose_cuda_set_step_scale(tpose::context, ss == "auto" ? (450.0f / rh) * (450.0f / rh) : (float)atof(ss.c_str())), "stepscale");
 
     const auto t0 = std::chrono::steady_clock::now();
     const auto rep = tpose::schedule::warp(ta, tb, frames);

@@ -41,11 +41,11 @@ EXPORTS = [
     "tpose_cuda_upload_points", "tpose_cuda_colors", "tpose_cuda_energy", "tpose_cuda_shift",
     "tpose_cuda_step", "tpose_cuda_run", "tpose_cuda_set_toterr", "tpose_cuda_get_toterr",
     "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
-    "tpose_cuda_raster_ids", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_set_kernel_timing", "tpose_cuda_sync",
+    "tpose_cuda_raster_ids", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_set_kernel_timing", "tpose_cuda_set_step_scale", "tpose_cuda_sync",
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
-    "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
+    "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_carry", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
     "tpose_cuda_mview_last_ms",
-    "tpose_cuda_watch", "tpose_cuda_read", "tpose_cuda_write", "tpose_cuda_batch_step", "tpose_cuda_batch_run",
+    "tpose_cuda_watch", "tpose_cuda_watch_mask", "tpose_cuda_read", "tpose_cuda_write", "tpose_cuda_batch_step", "tpose_cuda_batch_run",
 ]
 
 
@@ -209,6 +209,9 @@ class Context:
         self._ck(lib().tpose_cuda_last_elapsed_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def set_step_scale(self, scale):
+        self._ck(lib().tpose_cuda_set_step_scale(self._h, C.c_float(scale)))
+
     def set_kernel_timing(self, on):
         self._ck(lib().tpose_cuda_set_kernel_timing(self._h, C.c_int(1 if on else 0)))
 
@@ -314,6 +317,16 @@ def hdlt(PA, PB, A, B, device=0):
     X = np.zeros((A.shape[0], 4), np.float32)
     _mview_ck(lib().tpose_cuda_hdlt(device, _ptr(PA), _ptr(PB), _ptr(A), _ptr(B), A.shape[0], _ptr(X)), "hdlt")
     return X
+
+
+def carry(tri, frm, to, pts, ratio, device=0):
+    """triangulation::warp on the device: returns pts carried from embedding `frm` to embedding `to`."""
+    tri = np.ascontiguousarray(tri, np.int32); frm = np.ascontiguousarray(frm, np.float32)
+    to = np.ascontiguousarray(to, np.float32); out = np.ascontiguousarray(pts, np.float32).copy()
+    assert frm.shape == to.shape
+    _mview_ck(lib().tpose_cuda_carry(device, _ptr(tri), tri.shape[0], _ptr(frm), _ptr(to), frm.shape[0], _ptr(out),
+                                     out.shape[0], C.c_float(ratio)), "carry")
+    return out
 
 
 def mview_last_ms():

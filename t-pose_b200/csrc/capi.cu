@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of include/tpose_cuda.h over the sm_100a kernels.
 // There is no CPU path in this library: without a CUDA device every entry point fails.
 #include "../../include/tpose_cuda.h"
+#include "carry.cuh"
 #include "eval.cuh"
 #include "mview.cuh"
 #include "raster.cuh"
@@ -37,6 +38,7 @@ struct tpose_cuda_ctx {
     int maxT = 0, maxP = 0;
     int NT = 0, NP = 0;
     float ratio = 1.5f;
+    float step_scale = 1.0f;          // multiplies shift.cs's step constant (1 = the reference)
     bool have_mesh = false;
     ImageSlot img[2];
     uchar4* staging = nullptr; size_t staging_cap = 0;   // source-resolution upload buffer
@@ -56,7 +58,12 @@ struct tpose_cuda_ctx {
     int NE = 0, edges_np = 0;
     bool edges_dirty = true;
     std::vector<uint64_t> scratch_keys; std::vector<int32_t> scratch_i32;
-    int4* wtri = nullptr; int* whe = nullptr; bool watching = false;
+    int4* wtri = nullptr; int* whe = nullptr; unsigned* wmask = nullptr; bool watching = false;
+    // run_state | err_state | wmask | pts share one allocation ("report"), so that what a run's caller reads
+    // next -- verdict, watch mask, points -- comes back in a single copy
+    unsigned char* report = nullptr; size_t report_pts_off = 0; unsigned char* h_report = nullptr;
+    unsigned char* wbuf = nullptr;    // wtri | whe, packed at the current NT: one upload
+    unsigned* h_run_mask = nullptr; bool run_mask_valid = false;   // watch mask of the frame the last run stopped on
     unsigned* ticket = nullptr;       // [1] topology trigger accumulator ([0] spare)
     float* err_state = nullptr;       // [0] toterr [1] |relerr| [2] newerr [3] converged flag
     int* run_state = nullptr;         // RS_STOP, RS_STEPS, RS_TRIG
@@ -72,6 +79,9 @@ struct tpose_cuda_ctx {
     int group = 0;                    // lanes per edge (0 = pick from NT and H)
     std::vector<SeqGraph> graphs; uint64_t graph_clock = 0; bool use_graphs = true;
     bool mid_valid = false, time_kernels = false;
+    // read-back cache filled by tpose_cuda_run in the same synchronisation as its verdict: the points and
+    // toterr as the run left them (what the caller's next Buffer::retrieve / get_toterr would fetch)
+    float* h_run_pts = nullptr; bool run_cache_valid = false; float run_toterr = 0.0f;
     std::string err;
 };
 
@@ -99,6 +109,7 @@ static int fail(tpose_cuda_ctx* ctx, int code, const char* msg)
 static int upload_bytes(tpose_cuda_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
     if (bytes == 0) return TPOSE_OK;
+    ctx->run_cache_valid = false;
     if (bytes <= ctx->h_stage_cap) {
         const int slot = ctx->h_stage_next;
         ctx->h_stage_next = (slot + 1) % tpose_cuda_ctx::kStageSlots;
@@ -153,7 +164,15 @@ extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, 
     }
     const size_t nv = (size_t)kVariants * max_triangles;
 #define ALLOC(ptr, bytes) if ((e = cudaMalloc((void**)&(ptr), (bytes))) != cudaSuccess) return bail("cudaMalloc " #ptr, e)
-    ALLOC(ctx->pts, sizeof(float2) * max_points);
+    const size_t mask_words = ((size_t)max_triangles + 31) / 32;
+    ctx->report_pts_off = ((32 + sizeof(unsigned) * mask_words + 15) / 16) * 16;
+    ALLOC(ctx->report, ctx->report_pts_off + sizeof(float2) * max_points);
+    ctx->run_state = (int*)ctx->report;
+    ctx->err_state = (float*)(ctx->report + 16);
+    ctx->wmask = (unsigned*)(ctx->report + 32);
+    ctx->pts = (float2*)(ctx->report + ctx->report_pts_off);
+    ALLOC(ctx->wbuf, (sizeof(int4) + 3 * sizeof(int)) * (size_t)max_triangles);
+    ctx->wtri = (int4*)ctx->wbuf; ctx->whe = (int*)(ctx->wbuf + sizeof(int4) * (size_t)max_triangles);
     ALLOC(ctx->tri, sizeof(int4) * max_triangles);
     for (int s = 0; s < 2; s++) {
         ALLOC(ctx->cn[s], sizeof(int) * nv);
@@ -166,11 +185,7 @@ extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, 
     ALLOC(ctx->corner_off, sizeof(int) * ((size_t)max_points + 1));
     ALLOC(ctx->corners, sizeof(int) * 3 * (size_t)max_triangles);
     ALLOC(ctx->rec, sizeof(EdgeRec) * kEdgeMoves * 3 * (size_t)max_triangles);
-    ALLOC(ctx->wtri, sizeof(int4) * max_triangles);
-    ALLOC(ctx->whe, sizeof(int) * 3 * max_triangles);
     ALLOC(ctx->ticket, sizeof(unsigned) * 2);
-    ALLOC(ctx->err_state, sizeof(float) * 4);
-    ALLOC(ctx->run_state, sizeof(int) * 4);
     ALLOC(ctx->job_dev, sizeof(EvalJob));
 #undef ALLOC
     for (int s = 0; s < 2; s++) {
@@ -187,7 +202,7 @@ extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, 
     cudaEventCreate(&ctx->ev1);
     cudaEventCreate(&ctx->ev_mid);
     {
-        const size_t cap = std::max(sizeof(int4) * (size_t)max_triangles, sizeof(float2) * (size_t)max_points);
+        const size_t cap = std::max((sizeof(int4) + 3 * sizeof(int)) * (size_t)max_triangles, sizeof(float2) * (size_t)max_points);
         bool ok = cap <= (4u << 20);
         for (int i = 0; ok && i < tpose_cuda_ctx::kStageSlots; i++)
             ok = cudaHostAlloc((void**)&ctx->h_stage[i], cap, cudaHostAllocDefault) == cudaSuccess &&
@@ -211,11 +226,12 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     for (auto& s : ctx->img) { cudaFree(s.rgba); cudaFree(s.table); }
     for (int s = 0; s < 2; s++) { cudaFree(ctx->cn[s]); cudaFree(ctx->ca[s]); cudaFree(ctx->ten[s]); }
-    cudaFree(ctx->staging); cudaFree(ctx->pts); cudaFree(ctx->tri);
+    cudaFree(ctx->staging); cudaFree(ctx->tri);
     cudaFree(ctx->edges); cudaFree(ctx->tri_edges); cudaFree(ctx->corner_off); cudaFree(ctx->corners); cudaFree(ctx->rec);
-    cudaFree(ctx->gr); cudaFree(ctx->wtri); cudaFree(ctx->whe); cudaFree(ctx->ticket);
-    cudaFree(ctx->err_state); cudaFree(ctx->run_state); cudaFree(ctx->ids); cudaFree(ctx->flush);
+    cudaFree(ctx->gr); cudaFree(ctx->wbuf); cudaFree(ctx->ticket);
+    cudaFree(ctx->report); cudaFree(ctx->ids); cudaFree(ctx->flush);
     cudaFree(ctx->job_dev); cudaFree(ctx->batch_jobs);
+    if (ctx->h_report) cudaFreeHost(ctx->h_report);
     for (int i = 0; i < tpose_cuda_ctx::kStageSlots; i++) {
         if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
         if (ctx->h_stage_ev[i]) cudaEventDestroy(ctx->h_stage_ev[i]);
@@ -471,7 +487,7 @@ constexpr int kLaunchesPerEval = 2;
 // The host cannot issue two launches per step as fast as the device retires them, so sequences of
 // kGraphMinLen or more evaluations are captured once and replayed; the job records are read from
 // device memory at run time, so a captured sequence does not depend on the mesh or the image.
-constexpr int kGraphMinLen = 4;
+constexpr int kGraphMinLen = 2;
 constexpr size_t kGraphCacheSize = 24;
 
 static void issue_direct(const SeqKey& k, cudaStream_t st, cudaEvent_t mid = nullptr)
@@ -495,6 +511,7 @@ static bool same_key(const SeqKey& a, const SeqKey& b)
 
 static int issue_sequence(tpose_cuda_ctx* ctx, const SeqKey& key)
 {
+    ctx->run_cache_valid = false; ctx->run_mask_valid = false;
     ctx->launches += (int64_t)kLaunchesPerEval * key.len;
     if (key.len < kGraphMinLen || !ctx->use_graphs) {
         const bool mid = key.len == 1 && ctx->time_kernels;
@@ -567,11 +584,12 @@ static EvalJob make_job(const tpose_cuda_ctx* ctx, int slot, int flavour)
     j.rec = ctx->rec;
     j.ratio = ctx->ratio;
     j.dp = dp_for(ctx->NT, flavour);
-    j.step = flavour == TPOSE_WARP ? 0.00003f : 0.00005f;
+    j.step = (flavour == TPOSE_WARP ? 0.00003f : 0.00005f) * ctx->step_scale;
     for (int k = 0; k < 2; k++) { j.cn[k] = ctx->cn[k]; j.ca[k] = ctx->ca[k]; j.ten[k] = ctx->ten[k]; }
     j.gr = ctx->gr;
     j.wtri = ctx->watching ? ctx->wtri : nullptr;
     j.whe = ctx->watching ? ctx->whe : nullptr;
+    j.wmask = ctx->wmask;
     j.err_state = ctx->err_state; j.run_state = ctx->run_state;
     j.trig = ctx->ticket + 1;
     return j;
@@ -646,9 +664,10 @@ extern "C" int tpose_cuda_shift(tpose_cuda_ctx* ctx, int flavour)
     if (!ctx) return TPOSE_ERR_ARG;
     if (!ctx->have_mesh) return fail(ctx, TPOSE_ERR_STATE, "no mesh uploaded");
     CK(cudaSetDevice(ctx->device));
+    ctx->run_cache_valid = false;
     k_gradient<<<(ctx->NT + 127) / 128, 128, 0, ctx->stream>>>(ctx->tri, ctx->NT, ctx->ten[ctx->cur], ctx->gr);
     k_shift<<<(ctx->NP + 127) / 128, 128, 0, ctx->stream>>>(ctx->pts, ctx->NP, ctx->gr, ctx->ratio,
-                                                            flavour == TPOSE_WARP ? 0.00003f : 0.00005f);
+                                                            (flavour == TPOSE_WARP ? 0.00003f : 0.00005f) * ctx->step_scale);
     ctx->launches += 2;
     CK(cudaGetLastError());
     return TPOSE_OK;
@@ -694,9 +713,23 @@ extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int ma
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     int rs[4]; float es[4];
-    CK(cudaMemcpyAsync(rs, ctx->run_state, sizeof rs, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(es, ctx->err_state, sizeof es, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->h_report && cudaHostAlloc((void**)&ctx->h_report, ctx->report_pts_off + sizeof(float2) * (size_t)ctx->maxP, cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError(); ctx->h_report = nullptr;
+    }
+    if (ctx->h_report) {
+        // verdict + watch mask + points in one copy (the mask region is sized for maxT: a few KB)
+        CK(cudaMemcpyAsync(ctx->h_report, ctx->report, ctx->report_pts_off + sizeof(float2) * (size_t)ctx->NP, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(rs, ctx->h_report, sizeof rs); memcpy(es, ctx->h_report + 16, sizeof es);
+        ctx->h_run_mask = (unsigned*)(ctx->h_report + 32);
+        ctx->h_run_pts = (float*)(ctx->h_report + ctx->report_pts_off);
+    } else {
+        CK(cudaMemcpyAsync(rs, ctx->run_state, sizeof rs, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(es, ctx->err_state, sizeof es, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->run_cache_valid = ctx->h_report != nullptr; ctx->run_toterr = es[0];
+    ctx->run_mask_valid = ctx->h_report && ctx->watching && (rs[RS_TRIG] & kTrigTopology);
     if (rs[RS_STEPS] > 0) ctx->cur = (first + rs[RS_STEPS] - 1) & 1;
     if (steps_done) *steps_done = rs[RS_STEPS];
     if (trigger_flags) *trigger_flags = (uint32_t)rs[RS_TRIG];
@@ -707,15 +740,19 @@ extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int ma
 extern "C" int tpose_cuda_set_toterr(tpose_cuda_ctx* ctx, float toterr)
 {
     if (!ctx) return TPOSE_ERR_ARG;
+    if (ctx->run_cache_valid && ctx->run_toterr == toterr) return TPOSE_OK;   // the device already holds this value
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(ctx->err_state, &toterr, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    const bool keep = ctx->run_cache_valid;
+    int rc = upload_bytes(ctx, ctx->err_state, &toterr, sizeof(float));
+    if (rc) return rc;
+    ctx->run_cache_valid = keep; ctx->run_toterr = toterr;
     return TPOSE_OK;
 }
 
 extern "C" int tpose_cuda_get_toterr(tpose_cuda_ctx* ctx, float* toterr)
 {
     if (!ctx || !toterr) return TPOSE_ERR_ARG;
+    if (ctx->run_cache_valid) { *toterr = ctx->run_toterr; return TPOSE_OK; }
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(toterr, ctx->err_state, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -734,10 +771,34 @@ extern "C" int tpose_cuda_watch(tpose_cuda_ctx* ctx, const int32_t* tri_xyzw, co
             if (v < 0 || v >= ctx->NP || h < -1 || h >= 3 * nt) return fail(ctx, TPOSE_ERR_ARG, "watch: index out of range");
         }
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(ctx->wtri, tri_xyzw, sizeof(int4) * nt, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->whe, halfedges, sizeof(int) * 3 * nt, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    const bool keep = ctx->run_cache_valid;
+    // wtri | whe packed back to back at this NT, staged together: one H2D copy
+    ctx->whe = (int*)(ctx->wbuf + sizeof(int4) * (size_t)nt);
+    const size_t b_tri = sizeof(int4) * (size_t)nt, b_he = sizeof(int) * 3 * (size_t)nt;
+    if (b_tri + b_he <= ctx->h_stage_cap) {
+        const int slot = ctx->h_stage_next;
+        ctx->h_stage_next = (slot + 1) % tpose_cuda_ctx::kStageSlots;
+        CK(cudaEventSynchronize(ctx->h_stage_ev[slot]));
+        memcpy(ctx->h_stage[slot], tri_xyzw, b_tri);
+        memcpy(ctx->h_stage[slot] + b_tri, halfedges, b_he);
+        CK(cudaMemcpyAsync(ctx->wbuf, ctx->h_stage[slot], b_tri + b_he, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->h_stage_ev[slot], ctx->stream));
+    } else {
+        int rc = upload_bytes(ctx, ctx->wtri, tri_xyzw, b_tri);
+        if (!rc) rc = upload_bytes(ctx, ctx->whe, halfedges, b_he);
+        if (rc) return rc;
+    }
+    ctx->run_cache_valid = keep;
     ctx->watching = true;
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_watch_mask(tpose_cuda_ctx* ctx, uint32_t* mask_words, int nwords)
+{
+    if (!ctx || !mask_words || nwords < 0) return TPOSE_ERR_ARG;
+    if (!ctx->run_mask_valid) return fail(ctx, TPOSE_ERR_STATE, "watch_mask: the last call was not a tpose_cuda_run that stopped on TPOSE_TRIG_TOPOLOGY");
+    const int have = (ctx->NT + 31) / 32;
+    for (int i = 0; i < nwords; i++) mask_words[i] = i < have ? ctx->h_run_mask[i] : 0u;
     return TPOSE_OK;
 }
 
@@ -757,6 +818,7 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
         if (ctxs[i]->device != lead->device) return fail(lead, TPOSE_ERR_ARG, "batch: contexts live on different devices");
         for (int k = 0; k < i; k++) if (ctxs[k] == ctxs[i]) return fail(lead, TPOSE_ERR_ARG, "batch: a context appears twice");
         if (ctxs[i] != lead) cudaStreamSynchronize(ctxs[i]->stream);   // its uploads are done before we touch its buffers
+        ctxs[i]->run_cache_valid = false;
         rc = rebuild_edges(ctxs[i]);
         if (rc) { if (ctxs[i] != lead) lead->err = "batch: job " + std::to_string(i) + ": " + ctxs[i]->err; return rc; }
         jobs[(size_t)i] = make_job(ctxs[i], slot, flavour);
@@ -887,6 +949,10 @@ extern "C" int tpose_cuda_read(tpose_cuda_ctx* ctx, int which, size_t first, siz
     if (first + count > cap) return fail(ctx, TPOSE_ERR_CAPACITY, "read: range exceeds the buffer");
     if (count == 0) return TPOSE_OK;
     if (!dev) { memset(out, 0, elem * count); return TPOSE_OK; }   // penergy / nring: dead in the reference
+    if (which == TPOSE_BUF_POINTS && ctx->run_cache_valid && first + count <= (size_t)ctx->NP) {
+        memcpy(out, ctx->h_run_pts + 2 * first, elem * count);     // fetched together with the run's verdict
+        return TPOSE_OK;
+    }
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(out, (char*)dev + elem * first, elem * count, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -900,6 +966,7 @@ extern "C" int tpose_cuda_write(tpose_cuda_ctx* ctx, int which, size_t first, si
     if (!in || !buffer_info(ctx, which, &elem, &cap, &dev)) return fail(ctx, TPOSE_ERR_ARG, "write: bad buffer or null input");
     if (first + count > cap) return fail(ctx, TPOSE_ERR_CAPACITY, "write: range exceeds the buffer");
     if (count == 0 || !dev) return TPOSE_OK;
+    ctx->run_cache_valid = false;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync((char*)dev + elem * first, in, elem * count, cudaMemcpyHostToDevice, ctx->stream));
     if (which == TPOSE_BUF_INDEX) {   // keep the host mirror the edge view is derived from
@@ -938,6 +1005,13 @@ extern "C" int tpose_cuda_last_elapsed_ms(tpose_cuda_ctx* ctx, float* ms)
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventSynchronize(ctx->ev1));
     CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_set_step_scale(tpose_cuda_ctx* ctx, float scale)
+{
+    if (!ctx || !(scale > 0.0f)) return TPOSE_ERR_ARG;
+    ctx->step_scale = scale;
     return TPOSE_OK;
 }
 
@@ -1131,6 +1205,28 @@ extern "C" int tpose_cuda_triangulate(int device, const float* F9, const float* 
     if (B_corr) MCK(cudaMemcpy(B_corr, dBc.p, n * sizeof(float2), cudaMemcpyDeviceToHost));
     cudaEventElapsedTime(&g_mview_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_carry(int device, const int32_t* tri_xyzw, int nt, const float* from_xy, const float* to_xy, int nv,
+                                float* pts_xy, int npts, float ratio)
+{
+    if (!tri_xyzw || !from_xy || !to_xy || !pts_xy || nt < 0 || nv < 0 || npts < 0) return mview_fail(TPOSE_ERR_ARG, "carry: bad arguments");
+    if (nt == 0 || nv == 0 || npts == 0) return TPOSE_OK;          // triangulation.hpp:467,495: nothing to do
+    for (int t = 0; t < nt; t++)
+        for (int k = 0; k < 3; k++)
+            if (tri_xyzw[4 * t + k] < 0 || tri_xyzw[4 * t + k] >= nv) return mview_fail(TPOSE_ERR_ARG, "carry: triangle references a vertex outside [0,nv)");
+    int rc = mview_device(device);
+    if (rc) return rc;
+    DevBuf dT, dF, dTo, dP;
+    MCK(dT.alloc(sizeof(int4) * nt)); MCK(dF.alloc(sizeof(float2) * nv)); MCK(dTo.alloc(sizeof(float2) * nv)); MCK(dP.alloc(sizeof(float2) * npts));
+    MCK(cudaMemcpy(dT.p, tri_xyzw, sizeof(int4) * nt, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dF.p, from_xy, sizeof(float2) * nv, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dTo.p, to_xy, sizeof(float2) * nv, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dP.p, pts_xy, sizeof(float2) * npts, cudaMemcpyHostToDevice));
+    k_carry<<<(npts + kCarryThreads - 1) / kCarryThreads, kCarryThreads>>>(dT.as<int4>(), nt, dF.as<float2>(), dTo.as<float2>(), dP.as<float2>(), npts, ratio);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpy(pts_xy, dP.p, sizeof(float2) * npts, cudaMemcpyDeviceToHost));
     return TPOSE_OK;
 }
 

@@ -73,6 +73,7 @@ struct EvalJob {
     EdgeRec* rec;              // NE*9 records
     const int4* wtri;          // watch topology (the host's triangles / halfedges), may be null
     const int* whe;
+    unsigned* wmask;           // one bit per watched triangle: set where a per-frame edit may apply
     float* err_state;          // [0] toterr [1] |relerr| [2] newerr [3] converged flag of the last check
     int* run_state;            // RS_*
     unsigned* trig;            // [0] topology trigger accumulator
@@ -271,11 +272,13 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
         // service block: the previous frame's host-side checks
         if (!(flags & EV_CHECK_PREV)) return;
         if (tid == 0) *J.trig = 0u;
+        if (J.wtri) for (int w = tid; w < (J.NT + 31) / 32; w += kEdgeThreads) J.wmask[w] = 0u;
         __syncthreads();
         if (tid == kEdgeThreads - 1) geterr_serial(J.ten[set ^ 1], J.NT, J.err_state, rel_tol);
         else if (J.wtri) {
             bool hit = false;
-            for (int t = tid; t < J.NT; t += kEdgeThreads - 1) hit |= watch_triangle(J, t);
+            for (int t = tid; t < J.NT; t += kEdgeThreads - 1)
+                if (watch_triangle(J, t)) { hit = true; atomicOr(&J.wmask[t >> 5], 1u << (t & 31)); }
             if (hit) atomicOr(J.trig, (unsigned)kTrigTopology);
         }
         return;

@@ -128,3 +128,35 @@ def test_ported_programs_write_the_same_files_as_the_library_calls(dev, synth, t
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "levels" in out.stdout, out.stdout + out.stderr
     assert os.path.getsize(paths[0] + ".tri.warp") == os.path.getsize(paths[0] + ".tri")
+
+
+def test_device_warp_equals_reference_warp_bit_for_bit(cuda_pkg, synth):
+    """tpose_cuda_carry (csrc/carry.cuh) against the reference's own triangulation::warp /
+    reversewarp (source/triangulation.hpp:465-520, compiled unmodified): random points, points on
+    the boundary, on vertices and on edges (which stay where they are), degenerate triangles."""
+    R = H.ref()
+    rng = np.random.default_rng(5)
+    for ntri, ratio in ((150, 1.5), (1000, 16 / 9), (3000, 16 / 9)):
+        R.set_ratio(ratio)
+        opts, tri, _ = synth.mesh_for(ntri, ratio)
+        pts = opts.copy()
+        inner = np.arange(len(pts)) >= 4
+        pts[inner] += rng.normal(0, 0.004, (inner.sum(), 2)).astype(np.float32)
+        pts[:, 0] = np.clip(pts[:, 0], -np.float32(ratio), np.float32(ratio)); pts[:, 1] = np.clip(pts[:, 1], -1, 1)
+        tri = tri.copy()
+        tri[5, :3] = (tri[5, 0], tri[5, 0], tri[5, 2])          # a zero-length side
+        pts[tri[7, 1]] = pts[tri[7, 0]]                         # two coincident vertices
+        q = np.stack([rng.uniform(-ratio, ratio, 4000), rng.uniform(-1, 1, 4000)], 1).astype(np.float32)
+        q[:50, 0] = np.float32(ratio); q[50:100, 1] = -1.0       # on the boundary: never moved
+        q[100:200] = opts[rng.integers(0, len(opts), 100)]       # exactly on vertices of the source embedding
+        e = rng.integers(0, len(tri), 100)
+        q[200:300] = (0.5 * (opts[tri[e, 0]] + opts[tri[e, 1]])).astype(np.float32)   # on edges (up to rounding)
+        t = H.Tri(R)
+        t.set(tri, np.full(3 * len(tri), -1, np.int32), pts, opts)
+        for reverse in (False, True):
+            want = t.warp(q, reverse=reverse)
+            frm, to = (pts, opts) if reverse else (opts, pts)
+            got = cuda_pkg.carry(tri, frm, to, q, float(np.float32(ratio)))
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (ntri, reverse, np.abs(got - want).max())
+            assert not np.array_equal(got, q)                    # something moved
+        t.close()
