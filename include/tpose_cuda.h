@@ -195,6 +195,13 @@ int tpose_cuda_write(tpose_cuda_ctx *ctx, int buffer, size_t first, size_t count
  * triangle.fs displays (triangulate/main.cpp:157-166). */
 int tpose_cuda_raster_ids(tpose_cuda_ctx *ctx, int slot, int32_t *ids_host);
 
+/* software/view without a window (view/main.cpp:104-121, view/shader/triangle.{vs,fs}): the NT
+ * triangles drawn flat in the colours of tcolaccbuf's base rows (what tpose_cuda_upload put there),
+ * on black, at corners mix(points, other_pts, s) -- other_pts_xy (NP vec2, e.g. originpoints) may be
+ * NULL for s = 0.  Same raster conventions as the step; rgba_host: raster_h*raster_w*4 bytes. */
+int tpose_cuda_render(tpose_cuda_ctx *ctx, int raster_w, int raster_h, const float *other_pts_xy, float s,
+                      uint8_t *rgba_host);
+
 /* Device time in milliseconds of the most recent step/run call on this
  * context, measured with CUDA events on the context's stream. */
 int tpose_cuda_last_elapsed_ms(tpose_cuda_ctx *ctx, float *ms);

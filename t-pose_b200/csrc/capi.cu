@@ -999,6 +999,39 @@ extern "C" int tpose_cuda_raster_ids(tpose_cuda_ctx* ctx, int slot, int32_t* ids
     return TPOSE_OK;
 }
 
+extern "C" int tpose_cuda_render(tpose_cuda_ctx* ctx, int raster_w, int raster_h, const float* other_pts_xy, float s, uint8_t* rgba_host)
+{
+    if (!ctx) return TPOSE_ERR_ARG;
+    if (!ctx->have_mesh) return fail(ctx, TPOSE_ERR_STATE, "render: no mesh uploaded");
+    if (!rgba_host || raster_w <= 0 || raster_h <= 0 || raster_w > TPOSE_MAX_WIDTH || raster_h > TPOSE_MAX_HEIGHT)
+        return fail(ctx, TPOSE_ERR_ARG, "render: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)raster_w * raster_h;
+    // scratch: ids (int) | colours (uchar4) | mixed points (float2)
+    const size_t need = npix * (sizeof(int) + sizeof(uchar4)) + sizeof(float2) * (size_t)ctx->NP;
+    if (ctx->ids_cap < need) { cudaFree(ctx->ids); ctx->ids = nullptr; ctx->ids_cap = 0; CK(cudaMalloc((void**)&ctx->ids, need)); ctx->ids_cap = need; }
+    uchar4* colours = (uchar4*)(ctx->ids + npix);
+    float2* mixed = (float2*)(colours + npix);
+    const float2* pos = ctx->pts;
+    if (other_pts_xy) {
+        // the other embedding goes through the (unused during display) gradient buffer's neighbour: stage it after `mixed`
+        CK(cudaMemcpyAsync(mixed, other_pts_xy, sizeof(float2) * ctx->NP, cudaMemcpyHostToDevice, ctx->stream));
+        k_mix_points<<<(ctx->NP + 127) / 128, 128, 0, ctx->stream>>>(ctx->pts, mixed, ctx->NP, s, mixed);
+        ctx->launches++;
+        pos = mixed;
+    }
+    CK(cudaMemsetAsync(ctx->ids, 0xFF, npix * sizeof(int), ctx->stream));
+    const int warps_per_block = 8;
+    k_raster_ids<<<(ctx->NT + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, ctx->stream>>>(
+        pos, ctx->tri, ctx->NT, ctx->ratio, raster_w, raster_h, ctx->ids);
+    k_flat_colors<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(ctx->ids, ctx->ca[ctx->cur], (int)npix, colours);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rgba_host, colours, npix * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TPOSE_OK;
+}
+
 extern "C" int tpose_cuda_last_elapsed_ms(tpose_cuda_ctx* ctx, float* ms)
 {
     if (!ctx || !ms) return TPOSE_ERR_ARG;

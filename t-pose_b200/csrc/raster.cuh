@@ -44,4 +44,30 @@ k_raster_ids(const float2* __restrict__ pts, const int4* __restrict__ tri, int N
     }
 }
 
+// ---- headless display (software/view of the reference) ---------------------------------------------
+// view/shader/triangle.vs:44-46: every corner is drawn at mix(p, op, s); glm::mix(x, y, a) = x*(1-a) + y*a
+__global__ void k_mix_points(const float2* __restrict__ p, const float2* __restrict__ op, int np, float s, float2* __restrict__ out)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= np) return;
+    const float2 a = p[v], b = op[v];
+    const float w = __fsub_rn(1.0f, s);
+    out[v] = make_float2(__fadd_rn(__fmul_rn(a.x, w), __fmul_rn(b.x, s)), __fadd_rn(__fmul_rn(a.y, w), __fmul_rn(b.y, s)));
+}
+
+// view/shader/triangle.fs:22-24 (mode 2): fragColor = vec3(ca[index].rgb) / 255 on a black clear
+// colour; an RGBA8 target stores that as the clamped integer.  ids < 0: nothing drawn there.
+__global__ void k_flat_colors(const int* __restrict__ ids, const int4* __restrict__ ca, int npix, uchar4* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const int t = ids[i];
+    uchar4 c = make_uchar4(0, 0, 0, 255);
+    if (t >= 0) {
+        const int4 v = ca[t];
+        c = make_uchar4((unsigned char)min(max(v.x, 0), 255), (unsigned char)min(max(v.y, 0), 255), (unsigned char)min(max(v.z, 0), 255), 255);
+    }
+    out[i] = c;
+}
+
 }  // namespace tpose_dev

@@ -128,6 +128,13 @@ def test_ported_programs_write_the_same_files_as_the_library_calls(dev, synth, t
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "levels" in out.stdout, out.stdout + out.stderr
     assert os.path.getsize(paths[0] + ".tri.warp") == os.path.getsize(paths[0] + ".tri")
+    # software/view, headless: one picture per level
+    exe_v = os.path.join(root, "t-pose_b200", "bin", "view")
+    out = subprocess.run([exe_v, "-t", paths[0] + ".tri", "-o", str(tmp_path / "shot"), "-height", "120"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "level 0" in out.stdout, out.stdout + out.stderr
+    shot = open(str(tmp_path / "shot.0.ppm"), "rb").read()
+    assert shot.startswith(b"P6\n180 120\n255\n") and len(shot) == len(b"P6\n180 120\n255\n") + 180 * 120 * 3
+    assert len(set(shot[-180 * 120 * 3:])) > 4                  # not a blank frame
 
 
 def test_device_warp_equals_reference_warp_bit_for_bit(cuda_pkg, synth):

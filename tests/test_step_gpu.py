@@ -317,3 +317,32 @@ def test_batch_equals_individual_contexts(cuda_pkg, synth, O):
         c.close()
     for c in ctxs:
         c.close()
+
+
+def test_headless_view_matches_the_id_raster(cuda_pkg, synth, O):
+    """tpose_cuda_render (software/view without a window): flat triangle colours where the oracle's
+    triangle-ID raster says a triangle is drawn, black elsewhere; s interpolates towards the other
+    embedding like view/shader/triangle.vs:44-46."""
+    w, h = 300, 200
+    ratio = w / h
+    pts, tri, _ = synth.mesh_for(150, ratio)
+    rng = np.random.default_rng(3)
+    colors = np.zeros((tri.shape[0], 4), np.int32)
+    colors[:, :3] = rng.integers(0, 256, (tri.shape[0], 3))
+    colors[3, :3] = (300, -5, 128)                                   # clamped like an RGBA8 target
+    colors[:, 3] = 1
+    c = _ctx(cuda_pkg)
+    c.upload(pts, tri, ratio, colors)
+    other = pts.copy()
+    other[4:] += rng.normal(0, 0.01, other[4:].shape).astype(np.float32)
+    for s in (0.0, 0.25, 1.0):
+        got = c.render(w, h, other, s)
+        f32 = np.float32
+        mixed = (pts * (f32(1.0) - f32(s))).astype(f32) + (other * f32(s)).astype(f32)
+        ids = O.raster_ids(mixed.astype(f32), tri, ratio, w, h)
+        want = np.zeros((h, w, 4), np.uint8); want[..., 3] = 255
+        drawn = ids >= 0
+        want[drawn, :3] = np.clip(colors[ids[drawn], :3], 0, 255).astype(np.uint8)
+        assert np.array_equal(got, want), (s, int((got != want).any(axis=2).sum()))
+    assert np.array_equal(c.render(w, h), c.render(w, h, other, 0.0))
+    c.close()
