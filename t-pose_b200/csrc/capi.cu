@@ -487,7 +487,7 @@ constexpr int kLaunchesPerEval = 2;
 // The host cannot issue two launches per step as fast as the device retires them, so sequences of
 // kGraphMinLen or more evaluations are captured once and replayed; the job records are read from
 // device memory at run time, so a captured sequence does not depend on the mesh or the image.
-constexpr int kGraphMinLen = 2;
+constexpr int kGraphMinLen = 1;
 constexpr size_t kGraphCacheSize = 24;
 
 static void issue_direct(const SeqKey& k, cudaStream_t st, cudaEvent_t mid = nullptr)
@@ -513,7 +513,7 @@ static int issue_sequence(tpose_cuda_ctx* ctx, const SeqKey& key)
 {
     ctx->run_cache_valid = false; ctx->run_mask_valid = false;
     ctx->launches += (int64_t)kLaunchesPerEval * key.len;
-    if (key.len < kGraphMinLen || !ctx->use_graphs) {
+    if (key.len < kGraphMinLen || !ctx->use_graphs || (key.len == 1 && ctx->time_kernels)) {
         const bool mid = key.len == 1 && ctx->time_kernels;
         issue_direct(key, ctx->stream, mid ? ctx->ev_mid : nullptr);
         ctx->mid_valid = mid;
