@@ -60,8 +60,8 @@ int main(int argc, char* args[])
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::cout << "frames " << rep.frames << " (host body on " << rep.host_frames << "), splits " << rep.splits
               << ", flips " << rep.flips << ", prunes " << rep.prunes << ", collapses " << rep.collapses << ", idle host frames "
-              << rep.idle_host_frames << ", exports " << rep.exports << ", " << tr.NT << " triangles, " << sec << " s, "
-              << rep.frames / sec << " steps/s" << std::endl;
+              << rep.idle_host_frames << ", exports " << rep.exports << ", " << tr.NT << " triangles, " << sec << " s ("
+              << rep.s_device << " in tpose_cuda_run, " << rep.s_host << " in the host body), " << rep.frames / sec << " steps/s" << std::endl;
 
     tpose::quit();
     return 0;

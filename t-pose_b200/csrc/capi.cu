@@ -488,7 +488,7 @@ constexpr int kLaunchesPerEval = 2;
 // kGraphMinLen or more evaluations are captured once and replayed; the job records are read from
 // device memory at run time, so a captured sequence does not depend on the mesh or the image.
 constexpr int kGraphMinLen = 1;
-constexpr size_t kGraphCacheSize = 24;
+constexpr size_t kGraphCacheSize = 64;
 
 static void issue_direct(const SeqKey& k, cudaStream_t st, cudaEvent_t mid = nullptr)
 {

@@ -268,6 +268,9 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
     if ((flags & EV_HONOUR_STOP) && __ldcg(&J.run_state[RS_STOP])) return;
     set ^= J.flip;
 
+    // the last evaluation of a run only carries the checks of the last frame: nothing to integrate
+    if ((flags & EV_FINAL) && blockIdx.x != gridDim.x - 1) return;
+
     if (blockIdx.x == gridDim.x - 1) {
         // service block: the previous frame's host-side checks
         if (!(flags & EV_CHECK_PREV)) return;
@@ -417,6 +420,7 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags)
     int* const cn = J.cn[set]; int4* const ca = J.ca[set]; int* const ten = J.ten[set];
 
     const int nvb = (int)gridDim.x - kBaseBlocks;           // blocks that take vertices
+    if ((flags & EV_FINAL) && blockIdx.x != 0) return;      // check-only evaluation: block 0 records the verdict
     if ((int)blockIdx.x >= nvb) {
         // base variants, one thread each
         for (int t = ((int)blockIdx.x - nvb) * kCornerThreads + tid; t < J.NT; t += kBaseBlocks * kCornerThreads)
@@ -442,6 +446,7 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags)
         }
     }
 
+    if (flags & EV_FINAL) return;
     const int lane = tid & 31, c_in = lane >> 2, s = lane & 3;
     for (int v = (int)blockIdx.x * kCornerWarps + (tid >> 5); v < J.NP; v += nvb * kCornerWarps) {
         const int c0 = __ldg(J.corner_off + v), c1 = __ldg(J.corner_off + v + 1);
