@@ -346,3 +346,52 @@ def test_headless_view_matches_the_id_raster(cuda_pkg, synth, O):
         assert np.array_equal(got, want), (s, int((got != want).any(axis=2).sum()))
     assert np.array_equal(c.render(w, h), c.render(w, h, other, 0.0))
     c.close()
+
+
+def test_far_offscreen_vertices_take_the_wide_walk(cuda_pkg, O):
+    """Vertices thousands of rows outside the window (snap clamp at +-32768 px): edge heights beyond
+    2^22 sub-pixels send k_edges down its 64-bit remainder path; results still equal the oracle."""
+    rng = np.random.default_rng(21)
+    W, H = 96, 64
+    ratio = W / H
+    img = rng.integers(0, 256, size=(H, W, 4)).astype(np.uint8)
+    ctx = _ctx(cuda_pkg, 64, 256)
+    ctx.set_image(0, img)
+    for trial in range(12):
+        NT = 6
+        NP = 4 + 3 * NT
+        pts = np.stack([rng.uniform(-ratio, ratio, NP), rng.uniform(-1, 1, NP)], 1).astype(np.float32)
+        far = rng.choice(NP, 6, replace=False)
+        pts[far, 1] = rng.choice([-1.0, 1.0], 6) * rng.uniform(300, 1200, 6)      # up to 38 000 rows away (clamped)
+        pts[far[:2], 0] = rng.choice([-1.0, 1.0], 2) * rng.uniform(200, 900, 2)
+        tri = np.zeros((NT, 4), np.int32)
+        tri[:, :3] = rng.integers(0, NP, size=(NT, 3))
+        for fl in (cuda_pkg.TRIANGULATE, cuda_pkg.WARP):
+            cols = rng.integers(0, 256, size=(NT, 4)).astype(np.int32)
+            ctx.upload(pts, tri, ratio, cols)
+            ctx.step(0, fl, 1)
+            got = ctx.retrieve()
+            ref = O.step(img, pts, tri, ratio, fl, colors=cols)
+            _assert_step_equal(got, ref, ("cn", "ten"))
+    ctx.close()
+
+
+def test_maximum_width_image_takes_the_wide_sums(cuda_pkg, O):
+    """4095 x 2060 (the table's width limit; 255*W*H >= 2^31 switches k_edges to 64-bit colour sums),
+    saturated pixels, two triangles: counts, colour sums and (wrapping) energies equal the oracle."""
+    W, H = 4095, 2060
+    ratio = W / H
+    rng = np.random.default_rng(4)
+    img = np.full((H, W, 4), 255, np.uint8)
+    img[::7, ::5, :3] = rng.integers(0, 256, size=img[::7, ::5, :3].shape)
+    pts = np.array([[-ratio, -1], [-ratio, 1], [ratio, -1], [ratio, 1], [0.1, 0.05]], np.float32)
+    tri = np.array([[0, 1, 4, 0], [1, 3, 4, 0], [3, 2, 4, 0], [2, 0, 4, 0]], np.int32)
+    ctx = _ctx(cuda_pkg, 64, 64)
+    ctx.set_image(0, img)
+    ctx.upload(pts, tri, ratio)
+    ctx.step(0, cuda_pkg.TRIANGULATE, 1)
+    got = ctx.retrieve()
+    ref = O.step(img, pts, tri, ratio, O.TRIANGULATE)
+    _assert_step_equal(got, ref, ("cn", "ca", "ten"))
+    assert int(got["cn"][:4].sum()) == W * H
+    ctx.close()
