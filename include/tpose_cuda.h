@@ -157,6 +157,21 @@ int tpose_cuda_get_toterr(tpose_cuda_ctx *ctx, float *toterr);
  * something.  tri_xyzw == NULL switches the watch off.  halfedges: 3*nt twins or -1. */
 int tpose_cuda_watch(tpose_cuda_ctx *ctx, const int32_t *tri_xyzw, const int32_t *halfedges, int nt);
 
+/* Per-frame history of tpose_cuda_run (frames > 0 switches it on for runs of up to `frames` steps,
+ * 0 off).  The reference looks at every frame on the host: it reads the points back and runs its
+ * three edit loops (triangulate/main.cpp:199-346).  With the history on, a run records for each of
+ * its frames the points the frame left, the base energies it evaluated, toterr after its geterr
+ * and the watch mask at its points, and returns them with its verdict in one synchronisation, so
+ * the caller can replay its per-frame host code over a whole run afterwards.  Because the 0.8*pi
+ * flips never change what is uploaded, such a run no longer stops for them: TPOSE_TRIG_TOPOLOGY
+ * then means a prune or collapse may apply (conservatively, against the watch topology as given --
+ * the caller, whose own flips re-shape triangles during the replay, must check those itself). */
+int tpose_cuda_set_history(tpose_cuda_ctx *ctx, int frames);
+/* Frame `frame` (0 .. steps_done-1) of the last tpose_cuda_run; any output may be NULL.
+ * pts_xy: NP vec2; mask_words: as tpose_cuda_watch_mask; ten_base: NT int32; toterr: 1 float. */
+int tpose_cuda_history_frame(tpose_cuda_ctx *ctx, int frame, float *pts_xy, uint32_t *mask_words, int nwords,
+                             int32_t *ten_base, float *toterr);
+
 /* After a tpose_cuda_run that stopped with TPOSE_TRIG_TOPOLOGY: one bit per triangle of the watch
  * topology (bit t&31 of word t>>5), set where the device's conservative test fired on the frame
  * the run stopped on -- a superset of the triangles on which prune / the 0.8*pi flip / collapse can

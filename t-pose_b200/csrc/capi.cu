@@ -64,6 +64,10 @@ struct tpose_cuda_ctx {
     unsigned char* report = nullptr; size_t report_pts_off = 0; unsigned char* h_report = nullptr;
     unsigned char* wbuf = nullptr;    // wtri | whe, packed at the current NT: one upload
     unsigned* h_run_mask = nullptr; bool run_mask_valid = false;   // watch mask of the frame the last run stopped on
+    // per-frame history of tpose_cuda_run (tpose_cuda_set_history): device arrays + pinned host copies
+    int hist_cap = 0, hist_frames = 0, hist_np = 0, hist_nt = 0, hist_np_frames = 0;   // hist_np_frames: frames the last run recorded
+    float2* d_hist_pts = nullptr; int* d_hist_ten = nullptr; float* d_hist_err = nullptr; unsigned* d_hist_mask = nullptr;
+    float2* h_hist_pts = nullptr; int* h_hist_ten = nullptr; float* h_hist_err = nullptr; unsigned* h_hist_mask = nullptr;
     unsigned* ticket = nullptr;       // [1] topology trigger accumulator ([0] spare)
     float* err_state = nullptr;       // [0] toterr [1] |relerr| [2] newerr [3] converged flag
     int* run_state = nullptr;         // RS_STOP, RS_STEPS, RS_TRIG
@@ -232,6 +236,11 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
     cudaFree(ctx->report); cudaFree(ctx->ids); cudaFree(ctx->flush);
     cudaFree(ctx->job_dev); cudaFree(ctx->batch_jobs);
     if (ctx->h_report) cudaFreeHost(ctx->h_report);
+    cudaFree(ctx->d_hist_pts); cudaFree(ctx->d_hist_ten); cudaFree(ctx->d_hist_err); cudaFree(ctx->d_hist_mask);
+    if (ctx->h_hist_pts) cudaFreeHost(ctx->h_hist_pts);
+    if (ctx->h_hist_ten) cudaFreeHost(ctx->h_hist_ten);
+    if (ctx->h_hist_err) cudaFreeHost(ctx->h_hist_err);
+    if (ctx->h_hist_mask) cudaFreeHost(ctx->h_hist_mask);
     for (int i = 0; i < tpose_cuda_ctx::kStageSlots; i++) {
         if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
         if (ctx->h_stage_ev[i]) cudaEventDestroy(ctx->h_stage_ev[i]);
@@ -456,27 +465,27 @@ static EvalShape make_shape(int group, int max_np, int max_ne, bool narrow)
 }
 
 template <int G>
-static void launch_edges(const EvalJob* jobs, int njobs, const EvalShape& sh, int set, unsigned flags, double tol, cudaStream_t st)
+static void launch_edges(const EvalJob* jobs, int njobs, const EvalShape& sh, int set, unsigned flags, double tol, int frame, cudaStream_t st)
 {
     const dim3 grid(sh.grid_e + 1, njobs);   // + the service block
-    if (sh.narrow) k_edges<G, unsigned><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol);
-    else k_edges<G, unsigned long long><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol);
+    if (sh.narrow) k_edges<G, unsigned><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame);
+    else k_edges<G, unsigned long long><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame);
 }
 
 // one evaluation of every job: k_edges then k_corners
-static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int set, unsigned flags, double tol, cudaStream_t st,
+static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int set, unsigned flags, double tol, int frame, cudaStream_t st,
                         cudaEvent_t mid = nullptr)
 {
     switch (sh.group) {
-    case 1: launch_edges<1>(jobs, njobs, sh, set, flags, tol, st); break;
-    case 2: launch_edges<2>(jobs, njobs, sh, set, flags, tol, st); break;
-    case 4: launch_edges<4>(jobs, njobs, sh, set, flags, tol, st); break;
-    case 8: launch_edges<8>(jobs, njobs, sh, set, flags, tol, st); break;
-    case 16: launch_edges<16>(jobs, njobs, sh, set, flags, tol, st); break;
-    default: launch_edges<32>(jobs, njobs, sh, set, flags, tol, st); break;
+    case 1: launch_edges<1>(jobs, njobs, sh, set, flags, tol, frame, st); break;
+    case 2: launch_edges<2>(jobs, njobs, sh, set, flags, tol, frame, st); break;
+    case 4: launch_edges<4>(jobs, njobs, sh, set, flags, tol, frame, st); break;
+    case 8: launch_edges<8>(jobs, njobs, sh, set, flags, tol, frame, st); break;
+    case 16: launch_edges<16>(jobs, njobs, sh, set, flags, tol, frame, st); break;
+    default: launch_edges<32>(jobs, njobs, sh, set, flags, tol, frame, st); break;
     }
     if (mid) cudaEventRecord(mid, st);
-    k_corners<<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags);
+    k_corners<<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame);
 }
 constexpr int kLaunchesPerEval = 2;
 
@@ -498,7 +507,7 @@ static void issue_direct(const SeqKey& k, cudaStream_t st, cudaEvent_t mid = nul
             if (j > 0) f |= EV_CHECK_PREV;
             if (j == k.len - 1) f |= EV_FINAL;
         }
-        launch_eval(k.shape, k.jobs, k.njobs, (k.first_set + j) & 1, f, k.tol, st, mid);
+        launch_eval(k.shape, k.jobs, k.njobs, (k.first_set + j) & 1, f, k.tol, k.kind == 1 ? j : -1, st, mid);
     }
 }
 
@@ -590,6 +599,7 @@ static EvalJob make_job(const tpose_cuda_ctx* ctx, int slot, int flavour)
     j.wtri = ctx->watching ? ctx->wtri : nullptr;
     j.whe = ctx->watching ? ctx->whe : nullptr;
     j.wmask = ctx->wmask;
+    j.hist_pts = ctx->d_hist_pts; j.hist_ten = ctx->d_hist_ten; j.hist_err = ctx->d_hist_err; j.hist_mask = ctx->d_hist_mask;
     j.err_state = ctx->err_state; j.run_state = ctx->run_state;
     j.trig = ctx->ticket + 1;
     return j;
@@ -693,9 +703,9 @@ extern "C" int tpose_cuda_step(tpose_cuda_ctx* ctx, int slot, int flavour, int n
 // Evaluation j works on the points after j shifts, writes set (first+j)&1 and carries the checks of
 // frame j-1; evaluation max_steps is check-only.  See eval.cuh.
 static int issue_run(tpose_cuda_ctx* lead, const EvalJob* jobs, int njobs, const EvalShape& sh, int first_set,
-                     int flavour, int max_steps, double rel_tol)
+                     int flavour, int max_steps, double rel_tol, unsigned extra_flags = 0u)
 {
-    return issue_sequence(lead, SeqKey{jobs, njobs, sh, 1, max_steps + 1, first_set, fused_flags(flavour) | EV_HONOUR_STOP, rel_tol});
+    return issue_sequence(lead, SeqKey{jobs, njobs, sh, 1, max_steps + 1, first_set, fused_flags(flavour) | EV_HONOUR_STOP | extra_flags, rel_tol});
 }
 
 extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int max_steps, double rel_tol,
@@ -704,14 +714,25 @@ extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int ma
     int rc = check_ready(ctx, slot, flavour);
     if (rc) return rc;
     if (max_steps < 1) return fail(ctx, TPOSE_ERR_ARG, "run: max_steps < 1");
+    const bool hist = ctx->hist_frames > 0;
+    if (hist && max_steps > ctx->hist_frames) return fail(ctx, TPOSE_ERR_CAPACITY, "run: max_steps exceeds the history capacity (tpose_cuda_set_history)");
     rc = sync_job(ctx, slot, flavour);
     if (rc) return rc;
     CK(cudaMemsetAsync(ctx->run_state, 0, sizeof(int) * 4, ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     const int first = ctx->cur ^ 1;
-    rc = issue_run(ctx, ctx->job_dev, 1, shape_of(ctx, slot), first, flavour, max_steps, rel_tol);
+    rc = issue_run(ctx, ctx->job_dev, 1, shape_of(ctx, slot), first, flavour, max_steps, rel_tol, hist ? (unsigned)EV_HISTORY : 0u);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->hist_np_frames = 0;
+    if (hist) {     // every frame the run may have taken, in the same synchronisation as the verdict
+        const size_t f = (size_t)max_steps, words = ((size_t)ctx->NT + 31) / 32;
+        CK(cudaMemcpyAsync(ctx->h_hist_pts, ctx->d_hist_pts, sizeof(float2) * ctx->NP * f, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_hist_ten, ctx->d_hist_ten, sizeof(int) * ctx->NT * f, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_hist_err, ctx->d_hist_err, sizeof(float) * f, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_hist_mask, ctx->d_hist_mask, sizeof(unsigned) * words * f, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->hist_np = ctx->NP; ctx->hist_nt = ctx->NT;
+    }
     int rs[4]; float es[4];
     if (!ctx->h_report && cudaHostAlloc((void**)&ctx->h_report, ctx->report_pts_off + sizeof(float2) * (size_t)ctx->maxP, cudaHostAllocDefault) != cudaSuccess) {
         (void)cudaGetLastError(); ctx->h_report = nullptr;
@@ -729,11 +750,54 @@ extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int ma
         CK(cudaStreamSynchronize(ctx->stream));
     }
     ctx->run_cache_valid = ctx->h_report != nullptr; ctx->run_toterr = es[0];
-    ctx->run_mask_valid = ctx->h_report && ctx->watching && (rs[RS_TRIG] & kTrigTopology);
+    ctx->run_mask_valid = !hist && ctx->h_report && ctx->watching && (rs[RS_TRIG] & kTrigTopology);
+    if (hist) ctx->hist_np_frames = rs[RS_STEPS];
     if (rs[RS_STEPS] > 0) ctx->cur = (first + rs[RS_STEPS] - 1) & 1;
     if (steps_done) *steps_done = rs[RS_STEPS];
     if (trigger_flags) *trigger_flags = (uint32_t)rs[RS_TRIG];
     if (last_err) *last_err = es[1];
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_set_history(tpose_cuda_ctx* ctx, int frames)
+{
+    if (!ctx || frames < 0) return TPOSE_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (frames > ctx->hist_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_hist_pts); cudaFree(ctx->d_hist_ten); cudaFree(ctx->d_hist_err); cudaFree(ctx->d_hist_mask);
+        if (ctx->h_hist_pts) cudaFreeHost(ctx->h_hist_pts);
+        if (ctx->h_hist_ten) cudaFreeHost(ctx->h_hist_ten);
+        if (ctx->h_hist_err) cudaFreeHost(ctx->h_hist_err);
+        if (ctx->h_hist_mask) cudaFreeHost(ctx->h_hist_mask);
+        ctx->d_hist_pts = nullptr; ctx->d_hist_ten = nullptr; ctx->d_hist_err = nullptr; ctx->d_hist_mask = nullptr;
+        ctx->h_hist_pts = nullptr; ctx->h_hist_ten = nullptr; ctx->h_hist_err = nullptr; ctx->h_hist_mask = nullptr;
+        ctx->hist_cap = 0;
+        const size_t f = (size_t)frames, words = ((size_t)ctx->maxT + 31) / 32;
+        CK(cudaMalloc((void**)&ctx->d_hist_pts, sizeof(float2) * ctx->maxP * f));
+        CK(cudaMalloc((void**)&ctx->d_hist_ten, sizeof(int) * ctx->maxT * f));
+        CK(cudaMalloc((void**)&ctx->d_hist_err, sizeof(float) * f));
+        CK(cudaMalloc((void**)&ctx->d_hist_mask, sizeof(unsigned) * words * f));
+        CK(cudaHostAlloc((void**)&ctx->h_hist_pts, sizeof(float2) * ctx->maxP * f, cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&ctx->h_hist_ten, sizeof(int) * ctx->maxT * f, cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&ctx->h_hist_err, sizeof(float) * f, cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&ctx->h_hist_mask, sizeof(unsigned) * words * f, cudaHostAllocDefault));
+        ctx->hist_cap = frames;
+    }
+    ctx->hist_frames = frames;          // 0 switches the recording off (the buffers stay)
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_history_frame(tpose_cuda_ctx* ctx, int frame, float* pts_xy, uint32_t* mask_words, int nwords,
+                                        int32_t* ten_base, float* toterr)
+{
+    if (!ctx) return TPOSE_ERR_ARG;
+    if (frame < 0 || frame >= ctx->hist_np_frames) return fail(ctx, TPOSE_ERR_STATE, "history_frame: the last run recorded no such frame");
+    const size_t np = (size_t)ctx->hist_np, nt = (size_t)ctx->hist_nt, words = (nt + 31) / 32;
+    if (pts_xy) memcpy(pts_xy, ctx->h_hist_pts + (size_t)frame * np, sizeof(float2) * np);
+    if (ten_base) memcpy(ten_base, ctx->h_hist_ten + (size_t)frame * nt, sizeof(int) * nt);
+    if (toterr) *toterr = ctx->h_hist_err[frame];
+    if (mask_words) for (int i = 0; i < nwords; i++) mask_words[i] = (size_t)i < words ? ctx->h_hist_mask[(size_t)frame * words + i] : 0u;
     return TPOSE_OK;
 }
 

@@ -37,7 +37,8 @@ enum EvalFlags : unsigned {
     EV_GRAD_SHIFT  = 32u,  // gradient.cs + shift.cs fused behind the energies
     EV_CHECK_PREV  = 64u,  // previous frame's geterr + topology watch ride on this step
     EV_FINAL       = 128u, // last step of a run: checks only, never shifts
-    EV_HONOUR_STOP = 256u  // step is a no-op once the job's stop flag is up
+    EV_HONOUR_STOP = 256u, // step is a no-op once the job's stop flag is up
+    EV_HISTORY     = 512u  // record every frame (points, base energies, toterr, watch mask); flips alone do not stop the run
 };
 
 // trigger bits (mirrors include/tpose_cuda.h)
@@ -74,6 +75,11 @@ struct EvalJob {
     const int4* wtri;          // watch topology (the host's triangles / halfedges), may be null
     const int* whe;
     unsigned* wmask;           // one bit per watched triangle: set where a per-frame edit may apply
+    // per-frame history of a run (EV_HISTORY), frame f of the run at [f * NP], [f * NT], [f], [f * words]
+    float2* hist_pts;          // the points frame f left
+    int* hist_ten;             // the base energies frame f evaluated (what the reference reads back as terr)
+    float* hist_err;           // toterr after frame f's geterr
+    unsigned* hist_mask;       // the watch mask at the points frame f left
     float* err_state;          // [0] toterr [1] |relerr| [2] newerr [3] converged flag of the last check
     int* run_state;            // RS_*
     unsigned* trig;            // [0] topology trigger accumulator
@@ -118,7 +124,9 @@ __device__ __forceinline__ bool ccw(float2 A, float2 B, float2 C)
 }
 __device__ __forceinline__ int corner(const int4& t, int k) { return k == 0 ? t.x : (k == 1 ? t.y : t.z); }
 
-__device__ bool watch_triangle(const EvalJob& J, int t)
+// 0: nothing can apply; 1: only the 0.8*pi flip can (it never changes what is uploaded, so it needs
+// no stop by itself); 2: prune or collapse can -- or the watch data are inconsistent
+__device__ int watch_triangle(const EvalJob& J, int t)
 {
     const int4 tv = J.wtri[t];
     const float2 p[3] = {J.pts[tv.x], J.pts[tv.y], J.pts[tv.z]};
@@ -129,7 +137,7 @@ __device__ bool watch_triangle(const EvalJob& J, int t)
     for (int k = 0; k < 3; k++) cs[k] = angle_cos(p[k], p[(k + 1) % 3], p[(k + 2) % 3]);
     // (c) collapse (triangulation.hpp:330-340): shortest side <= 0.01 (tiny safety margin)
     const float l0 = vlen(vsub(p[1], p[0])), l1 = vlen(vsub(p[2], p[1])), l2 = vlen(vsub(p[0], p[2]));
-    if (fminf(l0, fminf(l1, l2)) <= 0.010001f) return true;
+    if (fminf(l0, fminf(l1, l2)) <= 0.010001f) return 2;
     // (a) prune (triangulation.hpp:220-241): all corners on the boundary, an open side, every
     //     angle outside (0, pi): acos argument not strictly inside (-1, 1)
     if (on_boundary(p[0], J.ratio) && on_boundary(p[1], J.ratio) && on_boundary(p[2], J.ratio) &&
@@ -137,7 +145,7 @@ __device__ bool watch_triangle(const EvalJob& J, int t)
         bool flat = true;
 #pragma unroll
         for (int k = 0; k < 3; k++) if (fabsf(cs[k]) < 0.99999f) flat = false;   // NaN compares false -> flat
-        if (flat) return true;
+        if (flat) return 2;
     }
     // (b) angle > 0.8*pi (main.cpp:325-334) with a flippable edge: twin exists and the quad is convex
 #pragma unroll
@@ -146,14 +154,14 @@ __device__ bool watch_triangle(const EvalJob& J, int t)
         const int hb = he[k];
         if (hb < 0) continue;
         const int tb = hb / 3, kb = hb - 3 * tb;
-        if (tb >= J.NT) return true;                            // inconsistent watch data: let the host look
+        if (tb >= J.NT) return 2;                               // inconsistent watch data: let the host look
         const int4 tvb = J.wtri[tb];
         const float2 A = p[k], C = p[(k + 2) % 3];
         const float2 B = J.pts[corner(tvb, kb)], D = J.pts[corner(tvb, (kb + 2) % 3)];
         if (ccw(A, C, D) == ccw(B, C, D) || ccw(A, B, C) == ccw(A, B, D)) continue;
-        return true;
+        return 1;
     }
-    return false;
+    return 0;
 }
 
 // geterr (source/triangulation.hpp:653-674): float32 running sum of the base energies in index
@@ -256,7 +264,7 @@ __device__ __forceinline__ void walk_edge(EdgeWalk& w, const uint4* __restrict__
 // G lanes per (edge, move) item.  The last block of each job's row is the service block.
 template <int G, typename ACC>
 __global__ void __launch_bounds__(kEdgeThreads)
-k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_tol)
+k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_tol, int frame)
 {
     __shared__ EvalJob J;
     const int tid = threadIdx.x;
@@ -275,13 +283,21 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
         // service block: the previous frame's host-side checks
         if (!(flags & EV_CHECK_PREV)) return;
         if (tid == 0) *J.trig = 0u;
-        if (J.wtri) for (int w = tid; w < (J.NT + 31) / 32; w += kEdgeThreads) J.wmask[w] = 0u;
+        const int words = (J.NT + 31) / 32;
+        const bool hist = (flags & EV_HISTORY) && frame > 0;          // this evaluation checks frame - 1
+        unsigned* const mask = hist ? J.hist_mask + (size_t)(frame - 1) * words : J.wmask;
+        if (J.wtri) for (int w = tid; w < words; w += kEdgeThreads) mask[w] = 0u;
         __syncthreads();
-        if (tid == kEdgeThreads - 1) geterr_serial(J.ten[set ^ 1], J.NT, J.err_state, rel_tol);
-        else if (J.wtri) {
+        if (tid == kEdgeThreads - 1) {
+            geterr_serial(J.ten[set ^ 1], J.NT, J.err_state, rel_tol);
+            if (hist) J.hist_err[frame - 1] = J.err_state[0];
+        } else if (J.wtri) {
             bool hit = false;
-            for (int t = tid; t < J.NT; t += kEdgeThreads - 1)
-                if (watch_triangle(J, t)) { hit = true; atomicOr(&J.wmask[t >> 5], 1u << (t & 31)); }
+            for (int t = tid; t < J.NT; t += kEdgeThreads - 1) {
+                const int code = watch_triangle(J, t);
+                if (code) atomicOr(&mask[t >> 5], 1u << (t & 31));
+                hit |= (flags & EV_HISTORY) ? code == 2 : code != 0;
+            }
             if (hit) atomicOr(J.trig, (unsigned)kTrigTopology);
         }
         return;
@@ -404,7 +420,7 @@ __device__ __forceinline__ int eval_variant(const EvalJob& J, unsigned flags, in
 }
 
 __global__ void __launch_bounds__(kCornerThreads)
-k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags)
+k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame)
 {
     __shared__ EvalJob J;
     const int tid = threadIdx.x;
@@ -423,8 +439,11 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags)
     if ((flags & EV_FINAL) && blockIdx.x != 0) return;      // check-only evaluation: block 0 records the verdict
     if ((int)blockIdx.x >= nvb) {
         // base variants, one thread each
-        for (int t = ((int)blockIdx.x - nvb) * kCornerThreads + tid; t < J.NT; t += kBaseBlocks * kCornerThreads)
-            eval_variant(J, flags, cn, ca, ten, t, 0);
+        const bool hist = (flags & EV_HISTORY) && frame >= 0 && !(flags & EV_FINAL);
+        for (int t = ((int)blockIdx.x - nvb) * kCornerThreads + tid; t < J.NT; t += kBaseBlocks * kCornerThreads) {
+            const int e = eval_variant(J, flags, cn, ca, ten, t, 0);
+            if (hist) J.hist_ten[(size_t)frame * J.NT + t] = e;       // harmless if this frame turns out to be discarded
+        }
         TL(1, 2);
         return;
     }
@@ -473,7 +492,8 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags)
         if (lane == 0 && !stop) {
             // shift.cs:16-47 (vertices nothing references get a zero gradient and are still clamped)
             J.gr[v] = make_int2((int)gx, (int)gy);
-            if (v >= 4) J.pts[v] = shift_vertex(p, (int)gx, (int)gy, J.ratio, J.step);
+            if (v >= 4) { p = shift_vertex(p, (int)gx, (int)gy, J.ratio, J.step); J.pts[v] = p; }
+            if ((flags & EV_HISTORY) && frame >= 0) J.hist_pts[(size_t)frame * J.NP + v] = p;
         }
     }
     TL(1, 4);
