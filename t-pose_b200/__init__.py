@@ -153,6 +153,24 @@ class Context:
         he = np.ascontiguousarray(halfedges, dtype=np.int32)
         self._ck(lib().tpose_cuda_watch(self._h, _ptr(tri), _ptr(he), tri.shape[0]))
 
+    def watch_mask(self):
+        """Bit t of the returned bool array: the device flagged triangle t on the frame the last run stopped on."""
+        nw = (self.NT + 31) // 32
+        m = np.zeros(nw, np.uint32)
+        self._ck(lib().tpose_cuda_watch_mask(self._h, _ptr(m), nw))
+        return np.unpackbits(m.view(np.uint8), bitorder="little")[:self.NT].astype(bool)
+
+    def set_history(self, frames):
+        self._ck(lib().tpose_cuda_set_history(self._h, C.c_int(frames)))
+
+    def history_frame(self, frame):
+        """Frame `frame` of the last run: dict(pts, mask (bool per triangle), ten (base energies), toterr)."""
+        nw = (self.NT + 31) // 32
+        pts = np.empty((self.NP, 2), np.float32); m = np.zeros(nw, np.uint32)
+        ten = np.empty(self.NT, np.int32); tot = C.c_float()
+        self._ck(lib().tpose_cuda_history_frame(self._h, C.c_int(frame), _ptr(pts), _ptr(m), nw, _ptr(ten), C.byref(tot)))
+        return dict(pts=pts, mask=np.unpackbits(m.view(np.uint8), bitorder="little")[:self.NT].astype(bool), ten=ten, toterr=tot.value)
+
     def read(self, which, first, count):
         dt, width = _BUF_DTYPE[which]
         out = np.empty((count, width) if width > 1 else (count,), dt)

@@ -395,3 +395,45 @@ def test_maximum_width_image_takes_the_wide_sums(cuda_pkg, O):
     _assert_step_equal(got, ref, ("cn", "ca", "ten"))
     assert int(got["cn"][:4].sum()) == W * H
     ctx.close()
+
+
+def test_run_history_equals_stepping_frame_by_frame(cuda_pkg, synth, O):
+    """tpose_cuda_set_history: every frame of a run -- points left, base energies evaluated, toterr
+    after its geterr, watch mask at its points -- equals what single-frame runs of a twin context
+    produce, and the recording does not change the run itself."""
+    w, h = 240, 160
+    ratio = w / h
+    img = synth.make_image(w, h, seed=41)
+    pts, tri, he = synth.mesh_for(150, ratio)
+    pts = pts.copy()
+    pts[60] = pts[61] + np.float32([0.02, 0.0])          # a short edge that the steps pull shorter
+    a = _ctx(cuda_pkg); b = _ctx(cuda_pkg)
+    for c in (a, b):
+        c.set_image(0, img); c.upload(pts, tri, ratio); c.watch(tri, he)
+    a.set_history(12)
+    n, flags, _ = a.run(0, cuda_pkg.TRIANGULATE, 12, 1e-12)
+    assert n >= 1
+    for f in range(n):
+        nb, fb, _ = b.run(0, cuda_pkg.TRIANGULATE, 1, 1e-12)          # one frame, looked at like the reference does
+        assert nb == 1
+        hf = a.history_frame(f)
+        rb = b.retrieve()
+        assert np.array_equal(bits(hf["pts"]), bits(rb["pts"])), f
+        assert np.array_equal(hf["ten"], rb["ten"][:tri.shape[0]]), f
+        assert hf["toterr"] == b.get_toterr(), f
+        if fb & cuda_pkg.TRIG_TOPOLOGY:
+            assert np.array_equal(hf["mask"], b.watch_mask()), f
+        else:
+            assert not hf["mask"].any(), f
+    # with the history on, the 0.8*pi flips alone do not stop a run; prune / collapse candidates do
+    if flags & cuda_pkg.TRIG_TOPOLOGY:
+        assert a.history_frame(n - 1)["mask"].any()
+    ra, rb = a.retrieve(), b.retrieve()
+    assert np.array_equal(bits(ra["pts"]), bits(rb["pts"])) and np.array_equal(ra["ten"], rb["ten"])
+    with pytest.raises(cuda_pkg.TposeCudaError):
+        a.run(0, cuda_pkg.TRIANGULATE, 13, 1e-12)         # beyond the history capacity
+    with pytest.raises(cuda_pkg.TposeCudaError):
+        a.history_frame(n)                                # not recorded
+    a.set_history(0)
+    a.run(0, cuda_pkg.TRIANGULATE, 20, 1e-12)             # off again: any length
+    a.close(); b.close()
