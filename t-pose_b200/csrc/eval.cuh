@@ -280,7 +280,20 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
     if ((flags & EV_FINAL) && blockIdx.x != gridDim.x - 1) return;
 
     if (blockIdx.x == gridDim.x - 1) {
-        // service block: the previous frame's host-side checks
+        // service block.  First: pull the static index arrays k_corners is about to chase through
+        // (corner lists, triangle -> edge map, triangles) into L2 while the edges are being walked;
+        // after a cold start each of them would otherwise cost k_corners a DRAM round trip in turn.
+        if (!(flags & EV_FINAL) && gridDim.y == 1) {      // (a batch keeps the memory system busy enough)
+            auto prefetch = [&](const void* base, size_t bytes) {
+                const char* p = reinterpret_cast<const char*>(base);
+                for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)kEdgeThreads * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+            };
+            prefetch(J.corner_off, sizeof(int) * ((size_t)J.NP + 1));
+            prefetch(J.corners, sizeof(int) * 3 * (size_t)J.NT);
+            prefetch(J.tri_edges, sizeof(int4) * (size_t)J.NT);
+        }
+        // then the previous frame's host-side checks
         if (!(flags & EV_CHECK_PREV)) return;
         if (tid == 0) *J.trig = 0u;
         const int words = (J.NT + 31) / 32;
