@@ -158,6 +158,29 @@ void tph_quit() { if (tpose::context) tpose::quit(); }
 void tph_texture(int slot, const unsigned char* rgba, int w, int h, int rw, int rh) { tpose::texture(slot, rgba, w, h, rw, rh); }
 void tph_upload(void* h, int uploadcolor) { tpose::upload((triangulation*)h, uploadcolor != 0); }
 
+// The per-frame edit loops of tpose/schedule on their own (host only).  mask32 == nullptr: the plain
+// loops of the reference; otherwise the sparse walk over the flagged triangles + `dirty` (64-bit words,
+// in/out).  counts: flips, prunes, collapses.  Returns 1 if the mesh must be uploaded again.
+int tph_frame_edits(void* h, const unsigned* mask32, int nwords, unsigned long long* dirty_words, int ndirty_words, long* counts3)
+{
+    auto* t = (triangulation*)h;
+    tpose::schedule::report rep;
+    tpose::schedule::detail::trimask cand, dirty;
+    dirty.reset(t->NT);
+    for (int i = 0; i < ndirty_words && i < (int)dirty.w.size(); i++) dirty.w[(size_t)i] = dirty_words[i];
+    bool updated;
+    if (mask32) {
+        cand.reset(t->NT);
+        for (int i = 0; i < nwords && (size_t)(i >> 1) < cand.w.size(); i++) cand.w[(size_t)i >> 1] |= (uint64_t)mask32[i] << (32 * (i & 1));
+        updated = tpose::schedule::detail::frame_edits(*t, rep, &cand, dirty);
+    } else {
+        updated = tpose::schedule::detail::frame_edits(*t, rep, nullptr, dirty);
+    }
+    for (int i = 0; i < ndirty_words; i++) dirty_words[i] = (size_t)i < dirty.w.size() ? dirty.w[(size_t)i] : 0ull;
+    counts3[0] = rep.flips; counts3[1] = rep.prunes; counts3[2] = rep.collapses;
+    return updated ? 1 : 0;
+}
+
 // report: frames, host_frames, runs, splits, exports, levels, finished
 void tph_triangulate(void* h, const int* exportlist, int nexport, const char* trifile, long max_frames, double tol, long* rep7)
 {

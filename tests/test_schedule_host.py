@@ -1,0 +1,103 @@
+"""The sparse per-frame edit loops of include/tpose/schedule (what the history replay runs) against
+the plain loops of the reference, on the host only: random meshes, several frames of drifting
+points, a conservative candidate mask computed -- like the device does -- against the topology of
+the LAST synchronisation (stale while the host keeps flipping), and the `dirty` set carried from
+frame to frame.  After every frame both meshes must be identical."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import hostlib as H
+
+
+def conservative_mask(tri, he, pts, ratio):
+    """numpy twin of watch_triangle (csrc/eval.cuh) without the convexity refinement: a superset of
+    the triangles on which prune / the 0.8*pi flip / collapse can act."""
+    NT = tri.shape[0]
+    p = pts[tri[:, :3]].astype(np.float32)                       # (NT, 3, 2)
+    flag = np.zeros(NT, bool)
+    for k in range(3):
+        a, b, c = p[:, k], p[:, (k + 1) % 3], p[:, (k + 2) % 3]
+        u, v = a - c, b - c
+        lu = np.sqrt((u * u).sum(1)); lv = np.sqrt((v * v).sum(1))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cs = (u * v).sum(1) / lu / lv
+        flag |= (cs < -0.80) & (he.reshape(NT, 3)[:, k] >= 0)
+        flag |= np.sqrt(((b - a) ** 2).sum(1)) <= 0.0101
+    on_b = (np.abs(p[..., 0]) >= np.float32(ratio)) | (np.abs(p[..., 1]) >= 1.0)
+    flag |= on_b.all(1) & (he.reshape(NT, 3) < 0).any(1)
+    return flag
+
+
+def pack32(flag):
+    nw = (len(flag) + 31) // 32
+    bits = np.zeros(nw * 32, np.uint8); bits[:len(flag)] = flag
+    return np.packbits(bits, bitorder="little").view(np.uint32).copy()
+
+
+def frame_edits(L, t, mask32, dirty):
+    counts = (C.c_long * 3)()
+    m = None if mask32 is None else mask32.ctypes.data_as(C.c_void_p)
+    upd = L.f("frame_edits")(t.h, m, 0 if mask32 is None else len(mask32), dirty.ctypes.data_as(C.c_void_p), len(dirty), counts)
+    return bool(upd), tuple(counts)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_sparse_frame_edits_equal_the_plain_loops(seed):
+    import importlib, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import __graft_entry__ as entry
+    entry.load_package()
+    synth = importlib.import_module("tpose_b200.synth")
+    L = H.ours()
+    rng = np.random.default_rng(100 + seed)
+    ratio = 1.5
+    L.set_ratio(ratio)
+    ntri = (150, 1000)[seed % 2]
+    pts, tri, he = synth.mesh_for(ntri, ratio)
+    pts = pts.copy()
+    inner = (np.abs(pts[:, 0]) < ratio) & (np.abs(pts[:, 1]) < 1)
+    cell = 2.0 / np.sqrt(ntri / 2)
+    pts[inner] += rng.normal(0, 0.45 * cell, (inner.sum(), 2)).astype(np.float32)      # slivers, inverted cells, short edges
+    # flat boundary triangles (prune candidates): pull the inner corner of a few border cells onto the border
+    r32 = np.float32(ratio)
+    on_right = pts[tri[:, :3], 0] >= r32
+    for t_ in np.flatnonzero(on_right.sum(1) == 2)[: 3 + seed % 3]:
+        pts[tri[t_, :3][~on_right[t_]][0], 0] = r32
+    plain, sparse = H.Tri(L), H.Tri(L)
+    for t in (plain, sparse):
+        t.set(tri, he, pts, pts)
+    dirty = np.zeros(64, np.uint64)
+    seen_tri, seen_he = tri.copy(), he.copy()          # the topology the "device" holds
+    total = [0, 0, 0]
+    for frame in range(10):
+        st = sparse.get()
+        cur = st["pts"]
+        if st["tri"].shape == seen_tri.shape:
+            mask = pack32(conservative_mask(seen_tri, seen_he, cur, ratio))
+        else:
+            raise AssertionError("a re-indexed mesh must have been re-synchronised")
+        up_p, cnt_p = frame_edits(L, plain, None, np.zeros(64, np.uint64))
+        up_s, cnt_s = frame_edits(L, sparse, mask, dirty)
+        assert (up_p, cnt_p) == (up_s, cnt_s), (frame, cnt_p, cnt_s)
+        a, b = plain.get(), sparse.get()
+        ok, where = H.same_state(a, b)
+        assert ok, (frame, where)
+        for i in range(3):
+            total[i] += cnt_p[i]
+        if up_s:                                       # prune / collapse: upload + watch, like the schedule does
+            dirty[:] = 0
+            seen_tri, seen_he = b["tri"].copy(), b["he"].copy()
+        elif frame % 4 == 3:                           # end of a run with flips only: watch
+            dirty[:] = 0
+            seen_tri, seen_he = b["tri"].copy(), b["he"].copy()
+        # the optimiser moves the points a little before the next frame
+        nxt = b["pts"].copy()
+        inner = (np.abs(nxt[:, 0]) < ratio) & (np.abs(nxt[:, 1]) < 1)
+        inner[:4] = False
+        nxt[inner] += rng.normal(0, 0.08 * cell, (inner.sum(), 2)).astype(np.float32)
+        plain.set_points(nxt); sparse.set_points(nxt)
+    assert total[0] > 0                                # the frames did flip things
+    plain.close(); sparse.close()
