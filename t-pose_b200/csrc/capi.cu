@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of include/tpose_cuda.h over the sm_100a kernels.
 // There is no CPU path in this library: without a CUDA device every entry point fails.
 #include "../../include/tpose_cuda.h"
+#include "../../include/tpose/detail/edgeview.h"
 #include "carry.cuh"
 #include "eval.cuh"
 #include "mview.cuh"
@@ -57,7 +58,7 @@ struct tpose_cuda_ctx {
     EdgeRec* rec = nullptr;
     int NE = 0, edges_np = 0;
     bool edges_dirty = true;
-    std::vector<uint64_t> scratch_keys; std::vector<int32_t> scratch_i32;
+    std::vector<uint64_t> scratch_keys; tpose::edgeview::view edge_view;
     int4* wtri = nullptr; int* whe = nullptr; unsigned* wmask = nullptr; bool watching = false;
     // run_state | err_state | wmask | pts share one allocation ("report"), so that what a run's caller reads
     // next -- verdict, watch mask, points -- comes back in a single copy
@@ -367,51 +368,15 @@ static int rebuild_edges(tpose_cuda_ctx* ctx)
     if (!ctx->edges_dirty) return TPOSE_OK;
     const int nt = ctx->NT, np = ctx->NP;
     if (ctx->tri_host.size() < (size_t)4 * nt) return fail(ctx, TPOSE_ERR_STATE, "index buffer mirror is incomplete");
-    const int32_t* tri = ctx->tri_host.data();
-    for (int t = 0; t < nt; t++)
-        for (int j = 0; j < 3; j++)
-            if (tri[4 * t + j] < 0 || tri[4 * t + j] >= np)
-                return fail(ctx, TPOSE_ERR_ARG, "index buffer references a vertex outside [0,NP)");
-    std::vector<uint64_t>& keys = ctx->scratch_keys;
-    keys.resize((size_t)3 * nt);
-    for (int t = 0; t < nt; t++)
-        for (int j = 0; j < 3; j++) {
-            const uint32_t x = (uint32_t)tri[4 * t + j], y = (uint32_t)tri[4 * t + (j + 1) % 3];
-            const uint32_t lo = x < y ? x : y, hi = x < y ? y : x;
-            // (lo, hi) in the top 42 bits (indices < 2^21), the side slot below
-            keys[(size_t)3 * t + j] = ((uint64_t)lo << 43) | ((uint64_t)hi << 22) | (uint64_t)(3 * t + j);
-        }
-    std::sort(keys.begin(), keys.end());
-    std::vector<int32_t>& buf = ctx->scratch_i32;
-    // layout of buf: edges (2 per edge, 6*nt reserved) | tri_edges (4*nt) | corner_off (np+1) | corners (3*nt)
-    const size_t o_edges = 0, o_te = (size_t)6 * nt, o_off = o_te + (size_t)4 * nt, o_cor = o_off + np + 1;
-    buf.assign(o_cor + (size_t)3 * nt, 0);
-    int ne = 0;
-    uint64_t prev = ~0ull;
-    for (size_t i = 0; i < keys.size(); i++) {
-        const uint64_t pair = keys[i] >> 22;
-        const int slot = (int)(keys[i] & 0x3FFFFFu), t = slot / 3, j = slot - 3 * t;
-        const int lo = (int)(pair >> 21), hi = (int)(pair & 0x1FFFFFu);
-        if (pair != prev) { buf[o_edges + 2 * ne] = lo; buf[o_edges + 2 * ne + 1] = hi; ne++; prev = pair; }
-        const bool rev = tri[4 * t + j] > tri[4 * t + (j + 1) % 3];
-        buf[o_te + 4 * t + j] = (ne - 1) | (rev ? (int32_t)0x80000000u : 0);
-    }
-    // corners grouped by vertex (counting sort): gradient.cs sums a vertex's contributions, the
-    // order inside a group is irrelevant (wrapping integer adds)
-    for (int t = 0; t < nt; t++)
-        for (int j = 0; j < 3; j++) buf[o_off + tri[4 * t + j] + 1]++;
-    for (int v = 0; v < np; v++) buf[o_off + v + 1] += buf[o_off + v];
-    {
-        std::vector<int32_t> fill(buf.begin() + (long)o_off, buf.begin() + (long)o_off + np);
-        for (int t = 0; t < nt; t++)
-            for (int j = 0; j < 3; j++) buf[o_cor + fill[tri[4 * t + j]]++] = (t << 2) | j;
-    }
-    CK(cudaMemcpyAsync(ctx->edges, &buf[o_edges], sizeof(int2) * ne, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->tri_edges, &buf[o_te], sizeof(int4) * nt, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->corner_off, &buf[o_off], sizeof(int) * (np + 1), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->corners, &buf[o_cor], sizeof(int) * 3 * nt, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));   // scratch is reused
-    ctx->NE = ne; ctx->edges_np = np;
+    tpose::edgeview::view& v = ctx->edge_view;
+    if (!tpose::edgeview::build(ctx->tri_host.data(), nt, np, v, ctx->scratch_keys))
+        return fail(ctx, TPOSE_ERR_ARG, "index buffer references a vertex outside [0,NP)");
+    CK(cudaMemcpyAsync(ctx->edges, v.edges.data(), sizeof(int2) * v.ne, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->tri_edges, v.tri_edges.data(), sizeof(int4) * nt, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->corner_off, v.corner_off.data(), sizeof(int) * (np + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->corners, v.corners.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // the view's vectors are reused
+    ctx->NE = v.ne; ctx->edges_np = np;
     ctx->edges_dirty = false;
     return TPOSE_OK;
 }

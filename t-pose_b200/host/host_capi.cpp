@@ -6,6 +6,7 @@
 #include <tpose/triangulation>
 #include <tpose/io>
 #include <tpose/schedule>
+#include <tpose/detail/edgeview.h>
 #include <tpose/multiview>
 
 #include <sstream>
@@ -157,6 +158,19 @@ int tph_init(int device)
 void tph_quit() { if (tpose::context) tpose::quit(); }
 void tph_texture(int slot, const unsigned char* rgba, int w, int h, int rw, int rh) { tpose::texture(slot, rgba, w, h, rw, rh); }
 void tph_upload(void* h, int uploadcolor) { tpose::upload((triangulation*)h, uploadcolor != 0); }
+
+// tpose/detail/edgeview.h on its own (host only).  Outputs sized by the caller: edges 6*nt, tri_edges 4*nt,
+// corner_off np+1, corners 3*nt.  Returns the number of unique edges, or -1 for a bad vertex index.
+int tph_edgeview(const int* tri4, int nt, int np, int* edges, int* tri_edges, int* corner_off, int* corners)
+{
+    tpose::edgeview::view v; std::vector<std::uint64_t> keys;
+    if (!tpose::edgeview::build(tri4, nt, np, v, keys)) return -1;
+    std::copy(v.edges.begin(), v.edges.end(), edges);
+    std::copy(v.tri_edges.begin(), v.tri_edges.end(), tri_edges);
+    std::copy(v.corner_off.begin(), v.corner_off.end(), corner_off);
+    std::copy(v.corners.begin(), v.corners.end(), corners);
+    return v.ne;
+}
 
 // The per-frame edit loops of tpose/schedule on their own (host only).  mask32 == nullptr: the plain
 // loops of the reference; otherwise the sparse walk over the flagged triangles + `dirty` (64-bit words,
