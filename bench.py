@@ -275,9 +275,8 @@ def run_ours(args):
     t0 = time.perf_counter()
     ctx.set_image(0, himg)
     for _ in range(Ke):
-        ctx.upload_points(hpts)                      # pointbuf->fill(points)
-        ctx.step(0, pkg.TRIANGULATE, 1)
-        ctx.retrieve_into(ten=hten, cn=hcn, pts=hpts)   # returns after the copies have landed
+        # pointbuf->fill(points) + step + read-backs, returns after the copies have landed
+        ctx.frame(0, pkg.TRIANGULATE, pts_in=hpts, ten=hten, cn=hcn, pts_out=hpts)
     ctx.sync()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     h2d = (img.nbytes / Ke) + pts.nbytes
@@ -318,8 +317,8 @@ def run_ours(args):
                          "frac_step_l2_warm": (balg / (warm_s / K) / 1e9) / peak},
             "e2e": {"value": world * Ke / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": Ke,
-                    "what": "set_image from pinned host memory once per job, then per frame pointbuf fill (H2D) + step + "
-                            "retrieve of tenergybuf, tcolnumbuf and pointbuf (13*NT ints each + NP vec2) through the C ABI"},
+                    "what": "set_image from pinned host memory once per job, then per frame tpose_cuda_frame: pointbuf fill (H2D) + "
+                            "step + read-back of tenergybuf, tcolnumbuf and pointbuf (13*NT ints each + NP vec2), one sync"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s_timed_region": time.perf_counter() - t_wall0,

@@ -129,6 +129,13 @@ int tpose_cuda_shift(tpose_cuda_ctx *ctx, int flavour);
  * i.e. exactly what the reference reads back at main.cpp:201-204. */
 int tpose_cuda_step(tpose_cuda_ctx *ctx, int slot, int flavour, int nsteps);
 
+/* One whole frame of the reference's loop in one call and one synchronisation
+ * (triangulate/main.cpp:196-204, warp/main.cpp:220-229): pointbuf->fill(pts_in_xy) if non-NULL, the
+ * fused step, then the frame's read-backs into whichever of ten13 / cn13 / ca13 / pts_out_xy are
+ * non-NULL (sizes as tpose_cuda_retrieve).  pts_in_xy may be reused when the call returns. */
+int tpose_cuda_frame(tpose_cuda_ctx *ctx, int slot, int flavour, const float *pts_in_xy,
+                     int32_t *ten13, int32_t *cn13, int32_t *ca13_rgba, float *pts_out_xy);
+
 /* Extension (default 1 = the reference): multiplies the step constant of shift.cs:45 (5e-5
  * triangulate, 3e-5 warp).  The integer gradient is a sum over pixels, so the reference's constant
  * -- tuned to its 800x450 window -- takes steps that grow with the pixel count: at 1920x1080 a

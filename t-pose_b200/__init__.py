@@ -39,7 +39,7 @@ EXPORTS = [
     "tpose_cuda_create", "tpose_cuda_destroy", "tpose_cuda_last_error", "tpose_cuda_version",
     "tpose_cuda_set_image", "tpose_cuda_set_image_device", "tpose_cuda_upload",
     "tpose_cuda_upload_points", "tpose_cuda_colors", "tpose_cuda_energy", "tpose_cuda_shift",
-    "tpose_cuda_step", "tpose_cuda_run", "tpose_cuda_set_toterr", "tpose_cuda_get_toterr",
+    "tpose_cuda_step", "tpose_cuda_frame", "tpose_cuda_run", "tpose_cuda_set_toterr", "tpose_cuda_get_toterr",
     "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
     "tpose_cuda_raster_ids", "tpose_cuda_render", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_set_kernel_timing", "tpose_cuda_set_step_scale", "tpose_cuda_sync",
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
@@ -137,6 +137,10 @@ class Context:
     # -- fused
     def step(self, slot, flavour, nsteps=1):
         self._ck(lib().tpose_cuda_step(self._h, slot, flavour, nsteps))
+
+    def frame(self, slot, flavour, pts_in=None, ten=None, cn=None, ca=None, pts_out=None):
+        """One reference frame: optional pointbuf fill, step, read-backs into caller-owned arrays."""
+        self._ck(lib().tpose_cuda_frame(self._h, slot, flavour, _ptr(pts_in), _ptr(ten), _ptr(cn), _ptr(ca), _ptr(pts_out)))
 
     def run(self, slot, flavour, max_steps, rel_tol):
         n, f, e = C.c_int(), C.c_uint32(), C.c_float()

@@ -665,6 +665,30 @@ extern "C" int tpose_cuda_step(tpose_cuda_ctx* ctx, int slot, int flavour, int n
 
 // Launch j evaluates the points after j shifts into set (first+j)&1 and carries the checks of frame
 // j-1; launch max_steps is check-only.  See eval.cuh.
+// One frame of the reference's loop as a single call (triangulate/main.cpp:196-204, warp/main.cpp:220-229):
+// optional pointbuf->fill, doenergy + doshift (+ the colours of the pipeline), and the read-backs the
+// frame ends with -- one stream synchronisation in all.
+extern "C" int tpose_cuda_frame(tpose_cuda_ctx* ctx, int slot, int flavour, const float* pts_in_xy,
+                                int32_t* ten13, int32_t* cn13, int32_t* ca13, float* pts_out_xy)
+{
+    int rc = check_ready(ctx, slot, flavour);
+    if (rc) return rc;
+    if (pts_in_xy && (rc = upload_bytes(ctx, ctx->pts, pts_in_xy, sizeof(float2) * ctx->NP)) != 0) return rc;
+    if ((rc = sync_job(ctx, slot, flavour)) != 0) return rc;
+    ctx->cur ^= 1;
+    rc = issue_sequence(ctx, SeqKey{ctx->job_dev, 1, shape_of(ctx, slot), 0, 1, ctx->cur, fused_flags(flavour), 0.0});
+    if (rc) return rc;
+    ctx->mid_valid = false;
+    const size_t nv = (size_t)kVariants * ctx->NT;
+    const int c = ctx->cur;
+    if (ten13) CK(cudaMemcpyAsync(ten13, ctx->ten[c], sizeof(int) * nv, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cn13) CK(cudaMemcpyAsync(cn13, ctx->cn[c], sizeof(int) * nv, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ca13) CK(cudaMemcpyAsync(ca13, ctx->ca[c], sizeof(int4) * nv, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pts_out_xy) CK(cudaMemcpyAsync(pts_out_xy, ctx->pts, sizeof(float2) * ctx->NP, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TPOSE_OK;
+}
+
 // Evaluation j works on the points after j shifts, writes set (first+j)&1 and carries the checks of
 // frame j-1; evaluation max_steps is check-only.  See eval.cuh.
 static int issue_run(tpose_cuda_ctx* lead, const EvalJob* jobs, int njobs, const EvalShape& sh, int first_set,

@@ -437,3 +437,32 @@ def test_run_history_equals_stepping_frame_by_frame(cuda_pkg, synth, O):
     a.set_history(0)
     a.run(0, cuda_pkg.TRIANGULATE, 20, 1e-12)             # off again: any length
     a.close(); b.close()
+
+
+def test_frame_call_equals_upload_step_retrieve(cuda_pkg, synth, O):
+    """tpose_cuda_frame = pointbuf fill + fused step + the frame's read-backs, in one call."""
+    w, h = 256, 160
+    ratio = w / h
+    img = synth.make_image(w, h, seed=9)
+    pts, tri, _ = synth.mesh_for(150, ratio)
+    nv = 13 * tri.shape[0]
+    a, b = _ctx(cuda_pkg), _ctx(cuda_pkg)
+    for c in (a, b):
+        c.set_image(0, img); c.upload(pts, tri, ratio)
+    cur = pts.copy()
+    ten = np.empty(nv, np.int32); cn = np.empty(nv, np.int32); ca = np.empty((nv, 4), np.int32); out = np.empty_like(pts)
+    for i in range(3):
+        a.frame(0, cuda_pkg.TRIANGULATE, pts_in=cur if i else None, ten=ten, cn=cn, ca=ca, pts_out=out)
+        if i:
+            b.upload_points(cur)
+        b.step(0, cuda_pkg.TRIANGULATE, 1)
+        r = b.retrieve()
+        assert np.array_equal(ten, r["ten"]) and np.array_equal(cn, r["cn"]) and np.array_equal(ca, r["ca"])
+        assert np.array_equal(bits(out), bits(r["pts"]))
+        cur = out.copy()
+        cur[10] += np.float32(0.001)                      # the host edits a point between frames
+    ref = O.step(img, pts, tri, ratio, O.TRIANGULATE)
+    a.upload(pts, tri, ratio)
+    a.frame(0, cuda_pkg.TRIANGULATE, ten=ten, pts_out=out)
+    assert np.array_equal(ten, ref["ten"]) and np.array_equal(bits(out), bits(ref["pts"]))
+    a.close(); b.close()
