@@ -103,9 +103,8 @@ def dist_setup(n):
     rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
-    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION writes it there) out of it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line: NCCL's banner / debug output (NCCL_DEBUG) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local, dist
 
