@@ -103,9 +103,21 @@ def dist_setup(n):
     rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
-    # stdout carries exactly one JSON line: NCCL's banner / debug output (NCCL_DEBUG) goes to stderr
+    # stdout carries exactly one JSON line.  NCCL writes its version banner (and any NCCL_DEBUG output)
+    # to file descriptor 1 while the communicator comes up, so fd 1 points at stderr until the first
+    # collective has run.
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     return rank, world, local, dist
 
 
