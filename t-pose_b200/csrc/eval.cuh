@@ -299,7 +299,7 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
         const int words = (J.NT + 31) / 32;
         const bool hist = (flags & EV_HISTORY) && frame > 0;          // this evaluation checks frame - 1
         unsigned* const mask = hist ? J.hist_mask + (size_t)(frame - 1) * words : J.wmask;
-        if (J.wtri) for (int w = tid; w < words; w += kEdgeThreads) mask[w] = 0u;
+        if (J.wtri || hist) for (int w = tid; w < words; w += kEdgeThreads) mask[w] = 0u;   // (no watch topology: an empty mask)
         __syncthreads();
         if (tid == kEdgeThreads - 1) {
             geterr_serial(J.ten[set ^ 1], J.NT, J.err_state, rel_tol);
