@@ -2,12 +2,12 @@
 wall times and size-independent checks (record sizes, level counts, half-edge consistency, F / 3-D
 points against the numpy oracle).  Writes gpurun_out/configs.json.
 
-  python tools/run_configs.py [--quick]      (--quick: 640x360, 500 triangles -- a smoke run)
+  python tests/run_configs.py [--quick]      (--quick: 640x360, 500 triangles -- a smoke run)
 """
 import argparse, json, os, struct, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))     # (this file lives in tests/ because it uses the oracle as its checker)
 import numpy as np
 import __graft_entry__ as entry
 import importlib

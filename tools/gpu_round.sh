@@ -22,5 +22,5 @@ TPOSE_CUDA_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,
 python tools/probe_step.py > gpurun_out/probe.log 2>&1
 python tools/probe_batch.py --batches 1,2,3,4,8,32,64,128 > gpurun_out/probe_batch.log 2>&1
 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
-timeout 300 python tools/run_configs.py --quick > gpurun_out/configs_quick.log 2>&1
+timeout 300 python tests/run_configs.py --quick > gpurun_out/configs_quick.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.json
