@@ -172,6 +172,16 @@ int tph_edgeview(const int* tri4, int nt, int np, int* edges, int* tri_edges, in
     return v.ne;
 }
 
+// The flip set of a converged frame (tpose/schedule, host only) from the energies in tpose::terr.
+// Returns the number of selected halfedges; he_out / energy_out sized 3*NT by the caller.
+int tph_flip_set(void* h, int* he_out, float* energy_out)
+{
+    ensure_mirrors();
+    const auto fs = tpose::schedule::detail::flip_set(*(triangulation*)h);
+    for (size_t i = 0; i < fs.size(); i++) { he_out[i] = fs[i].first; energy_out[i] = fs[i].second; }
+    return (int)fs.size();
+}
+
 // The per-frame edit loops of tpose/schedule on their own (host only).  mask32 == nullptr: the plain
 // loops of the reference; otherwise the sparse walk over the flagged triangles + `dirty` (64-bit words,
 // in/out).  counts: flips, prunes, collapses.  Returns 1 if the mesh must be uploaded again.

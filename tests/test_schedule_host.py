@@ -101,3 +101,37 @@ def test_sparse_frame_edits_equal_the_plain_loops(seed):
         plain.set_points(nxt); sparse.set_points(nxt)
     assert total[0] > 0                                # the frames did flip things
     plain.close(); sparse.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_flip_set_matches_the_std_set_semantics_of_the_reference(seed):
+    """detail::flip_set (stable sort + unique) against the literal restatement of the reference's
+    std::set / std::map logic (oracle/schedule_oracle._flip_set, triangulate/main.cpp:233-281), with
+    many tied energies -- the comparator's tie rule is behaviour."""
+    import importlib, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import __graft_entry__ as entry
+    entry.load_package()
+    synth = importlib.import_module("tpose_b200.synth")
+    from oracle import schedule_oracle as S
+    L = H.ours()
+    rng = np.random.default_rng(seed)
+    ratio = 1.5
+    L.set_ratio(ratio)
+    pts, tri, he = synth.mesh_for((150, 1000)[seed % 2], ratio)
+    nt = tri.shape[0]
+    t = H.Tri(L)
+    t.set(tri, he, pts, pts)
+    # few distinct values -> many equal sums; a couple of huge ones whose int sum wraps like the reference's
+    terr = rng.integers(0, 6 if seed < 4 else 2_000_000, nt).astype(np.int32)
+    terr[rng.integers(0, nt, 3)] = 2_000_000_000
+    L.f("set_terr")(terr.ctypes.data_as(C.c_void_p), nt)
+    out_h = np.zeros(3 * nt, np.int32); out_e = np.zeros(3 * nt, np.float32)
+    n = L.f("flip_set")(t.h, H._p(out_h), H._p(out_e))
+    with np.errstate(over="ignore"):
+        want = S._flip_set(terr, he, nt)
+    assert n == len(want) and n > 0
+    assert out_h[:n].tolist() == list(want.keys())
+    assert np.array_equal(out_e[:n], np.array(list(want.values()), np.float32))
+    t.close()
