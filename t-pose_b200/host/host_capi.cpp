@@ -172,6 +172,10 @@ int tph_edgeview(const int* tri4, int nt, int np, int* edges, int* tri_edges, in
     return v.ne;
 }
 
+// The two acos / sqrt-free pre-filters of the per-frame loops (tpose/schedule, host only)
+int tph_very_obtuse(void* h, int ha) { return tpose::schedule::detail::very_obtuse(*(triangulation*)h, ha) ? 1 : 0; }
+int tph_collapse_candidate(void* h, int ta) { return tpose::schedule::detail::collapse_candidate(*(triangulation*)h, ta); }
+
 // The flip set of a converged frame (tpose/schedule, host only) from the energies in tpose::terr.
 // Returns the number of selected halfedges; he_out / energy_out sized 3*NT by the caller.
 int tph_flip_set(void* h, int* he_out, float* energy_out)

@@ -135,3 +135,52 @@ def test_flip_set_matches_the_std_set_semantics_of_the_reference(seed):
     assert out_h[:n].tolist() == list(want.keys())
     assert np.array_equal(out_e[:n], np.array(list(want.values()), np.float32))
     t.close()
+
+
+def test_prefilters_decide_like_the_reference_predicates():
+    """detail::very_obtuse == (triangulation::angle(h) > 0.8*PI) and detail::collapse_candidate picks the
+    half-edge the reference's collapse loop would try (or -1 when collapse() would refuse it), on
+    triangles built to sit around both thresholds -- the reference's own angle()/hlength() (unmodified
+    headers, oracle/_ref) are the authority."""
+    import os
+    if not os.path.exists(H.REF_SO):
+        pytest.skip("oracle/_ref not built")
+    L, R = H.ours(), H.ref()
+    rng = np.random.default_rng(17)
+    ratio = 1.5
+    L.set_ratio(ratio); R.set_ratio(ratio)
+    n = 4000
+    # apex angle swept through 0.8*pi (144 deg) and side lengths through 0.01
+    ang = np.deg2rad(np.concatenate([rng.uniform(143.9, 144.1, n // 2), rng.uniform(100, 179.9, n // 2)]))
+    la = np.concatenate([rng.uniform(0.0099, 0.0101, n // 4), rng.uniform(0.002, 0.5, n - n // 4)])
+    lb = rng.uniform(0.005, 0.5, n)
+    rot = rng.uniform(0, 2 * np.pi, n)
+    apex = np.stack([rng.uniform(-1, 1, n), rng.uniform(-0.6, 0.6, n)], 1)
+    a = apex + la[:, None] * np.stack([np.cos(rot), np.sin(rot)], 1)
+    b = apex + lb[:, None] * np.stack([np.cos(rot + ang), np.sin(rot + ang)], 1)
+    pts = np.concatenate([a, b, apex]).astype(np.float32)
+    tri = np.zeros((n, 4), np.int32)
+    tri[:, 0] = np.arange(n); tri[:, 1] = np.arange(n) + n; tri[:, 2] = np.arange(n) + 2 * n     # half-edge 0 faces the apex
+    he = np.full(3 * n, -1, np.int32)
+    to, tr_ = H.Tri(L), H.Tri(R)
+    for t in (to, tr_):
+        t.set(tri, he, pts, pts)
+    pi32 = float(np.float32(3.14159265))                  # tpose::PI
+    hits = 0
+    for t in range(n):
+        for k in range(3):
+            want = float(np.float32(tr_.angle(3 * t + k))) > 0.8 * pi32
+            assert bool(L.f("very_obtuse")(to.h, 3 * t + k)) == want, (t, k)
+            hits += want
+        # the reference's loop: the first strictly shortest side; collapse() refuses it if longer than 0.01
+        ls = [float(np.float32(tr_.hlength(3 * t + k))) for k in range(3)]
+        ha = 0
+        if ls[1] < ls[ha]: ha = 1
+        if ls[ha + 1 if ha < 2 else 2] < ls[ha] and ha < 2: ha = ha + 1
+        got = L.f("collapse_candidate")(to.h, t)
+        if ls[ha] > 0.01:
+            assert got in (-1, 3 * t + ha), (t, got, ls)          # -1, or a candidate collapse() will refuse itself
+        else:
+            assert got == 3 * t + ha, (t, got, ls)
+    assert 500 < hits < 3 * n
+    to.close(); tr_.close()
