@@ -178,6 +178,11 @@ int tpose_cuda_set_history(tpose_cuda_ctx *ctx, int frames);
  * pts_xy: NP vec2; mask_words: as tpose_cuda_watch_mask; ten_base: NT int32; toterr: 1 float. */
 int tpose_cuda_history_frame(tpose_cuda_ctx *ctx, int frame, float *pts_xy, uint32_t *mask_words, int nwords,
                              int32_t *ten_base, float *toterr);
+/* Puts pgradbuf back to what frame `frame` of the last run left (device-side copy).  A caller that
+ * resumes from a recorded frame needs it: triangle.vs:93-98 zeroes the gradient only of vertices
+ * some triangle references, so a vertex the caller's edit leaves without triangles keeps -- and
+ * shift.cs keeps applying -- the entry of exactly that frame. */
+int tpose_cuda_history_restore_gradient(tpose_cuda_ctx *ctx, int frame);
 
 /* After a tpose_cuda_run that stopped with TPOSE_TRIG_TOPOLOGY: one bit per triangle of the watch
  * topology (bit t&31 of word t>>5), set where the device's conservative test fired on the frame

@@ -72,13 +72,21 @@ def mode0(rgba, pts, tri, ratio, flavour, ca=None):
     return cn, ca
 
 
-def mode1(rgba, pts, tri, ratio, flavour, cn, ca, NP=None):
+def mode1(rgba, pts, tri, ratio, flavour, cn, ca, NP=None, gr=None):
+    """gr: the gradient SSBO as the previous frame left it (None = all zero, a fresh tpose::init).
+    Mode 1 zeroes it only for vertices some triangle references (triangle.vs:93-98); a vertex no
+    triangle uses keeps its stale entry, and shift.cs goes on applying it."""
     rgba, pts, tri = _u8(rgba), _f32(pts), _i32(tri)
     H, W = rgba.shape[:2]
     NT = tri.shape[0]
     NP = pts.shape[0] if NP is None else NP
     ten = np.zeros(13 * NT, np.int32)
-    gr = np.zeros((NP, 2), np.int32)
+    if gr is None:
+        gr = np.zeros((NP, 2), np.int32)
+    else:
+        old = _i32(gr).reshape(-1, 2)
+        gr = np.zeros((max(NP, old.shape[0]), 2), np.int32)
+        gr[:old.shape[0]] = old
     lib().tpo_mode1(_p(rgba), W, H, _p(pts), _p(tri), NT, C.c_float(ratio), flavour,
                     _p(_i32(cn)), _p(_i32(ca)), _p(ten), _p(gr))
     return ten, gr
@@ -108,7 +116,21 @@ def sum_energy(ten, NT):
     return float(lib().tpo_sum_energy(_p(_i32(ten)), NT))
 
 
-def step(rgba, pts, tri, ratio, flavour, colors=None):
+def set_dp_law(which):
+    """-1: dp follows the flavour (the shipped shaders); 0 / 1: force the triangulate / warp cooling law."""
+    lib().tpo_set_dp_law(C.c_int(which))
+
+
+def resample(rgba, rw, rh):
+    """The raster image of the 1/1.5 window (see tpo_resample): (rh, rw, 4) uint8."""
+    rgba = _u8(rgba)
+    h, w = rgba.shape[:2]
+    out = np.empty((rh, rw, 4), np.uint8)
+    lib().tpo_resample(_p(rgba), w, h, _p(out), rw, rh)
+    return out
+
+
+def step(rgba, pts, tri, ratio, flavour, colors=None, gr=None):
     """One full evaluation + update at positions `pts`.
 
     Returns dict(cn, ca, ten, gr, pts) where cn/ca/ten are the 13*NT rows at
@@ -126,7 +148,7 @@ def step(rgba, pts, tri, ratio, flavour, colors=None):
         cn, _ = mode0(rgba, pts, tri, ratio, WARP, ca)
     else:
         cn, ca = mode0(rgba, pts, tri, ratio, TRIANGULATE)
-    ten, gr = mode1(rgba, pts, tri, ratio, flavour, cn, ca)
+    ten, gr = mode1(rgba, pts, tri, ratio, flavour, cn, ca, gr=gr)
     gr = gradient(tri, ten, gr)
-    new_pts = shift(pts, gr, ratio, flavour)
+    new_pts = shift(pts, gr[:_f32(pts).shape[0]], ratio, flavour)
     return dict(cn=cn, ca=ca, ten=ten, gr=gr, pts=new_pts)

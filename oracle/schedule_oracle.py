@@ -27,6 +27,7 @@ class _Device:
         self.cn = None
         self.ca = None
         self.ten = None
+        self.gr = None          # pgradbuf persists across frames and uploads (triangle.vs:93-98 zeroes referenced vertices only)
 
     def upload(self, tr_state, colors13=None):      # source/triangulation.hpp:628-643
         self.pts = tr_state["pts"].copy()
@@ -81,11 +82,11 @@ def triangulate_loop(R, Tri, img, ratio, exportlist, trifile, max_frames, tol=1e
         dev.cn, dev.ca = O.mode0(img, dev.pts, dev.tri, ratio, O.TRIANGULATE)
 
     def doenergy():                                             # main.cpp:132-141
-        dev.ten, dev.gr = O.mode1(img, dev.pts, dev.tri, ratio, O.TRIANGULATE, dev.cn, dev.ca)
+        dev.ten, dev.gr = O.mode1(img, dev.pts, dev.tri, ratio, O.TRIANGULATE, dev.cn, dev.ca, gr=dev.gr)
 
     def doshift():                                              # main.cpp:143-155
         dev.gr = O.gradient(dev.tri, dev.ten, dev.gr)
-        dev.pts = O.shift(dev.pts, dev.gr, ratio, O.TRIANGULATE)
+        dev.pts = O.shift(dev.pts, dev.gr[:len(dev.pts)], ratio, O.TRIANGULATE)
 
     def retrieve_terr():
         R.f("set_terr")(dev.ten.ctypes.data_as(C.c_void_p), len(dev.ten))
@@ -194,9 +195,10 @@ def warp_loop(R, Tri, img_a, img_b, triA, triB, max_frames, tol=1e-6):
         ratio = R.get_ratio()
         img = img_b if warpA else img_a                         # warp/shader/triangle.fs:49-50
         cn, _ = O.mode0(img, state["pts"], state["tri"], ratio, O.WARP, state["ca"])      # doreset
-        ten, gr = O.mode1(img, state["pts"], state["tri"], ratio, O.WARP, cn, state["ca"])  # doenergy
+        ten, gr = O.mode1(img, state["pts"], state["tri"], ratio, O.WARP, cn, state["ca"], gr=state.get("gr"))  # doenergy
         gr = O.gradient(state["tri"], ten, gr)                  # doshift
-        state["pts"] = O.shift(state["pts"], gr, ratio, O.WARP)
+        state["gr"] = gr
+        state["pts"] = O.shift(state["pts"], gr[:len(state["pts"])], ratio, O.WARP)
         frames += 1
         R.f("set_terr")(ten.ctypes.data_as(C.c_void_p), len(ten))
         tr.set_points(state["pts"])

@@ -52,10 +52,16 @@
 
 typedef struct { int32_t x[3], y[3]; } tpo_tri_fx;
 
+/* Test hook: the reference's own test programs ship shader copies with other cooling laws
+ * (tests/opt_min_energy_edgeflip/shader/triangle.vs:59-76).  which < 0: follow the flavour. */
+static int g_dp_law = -1;
+void tpo_set_dp_law(int which) { g_dp_law = which; }
+
 /* triangle.vs:60-62 (triangulate), warp/shader/triangle.vs:63-65 (warp) */
 float tpo_dp(int NT, int flavour)
 {
     float dp = 0.05f;
+    if (g_dp_law >= 0) flavour = g_dp_law;
     if (flavour == TPO_WARP) dp = dp / (1.0f + 9.0f * (float)NT / 1000.0f);
     else                     dp = dp / (1.0f + 4.0f * (float)NT / 3000.0f);
     return dp;
@@ -313,6 +319,42 @@ void tpo_frame_warp(const uint8_t *rgba_other, int W, int H, float *pts, int NP,
     tpo_mode1(rgba_other, W, H, pts, tri, NT, ratio, TPO_WARP, cn, ca, ten, gr);
     tpo_gradient(tri, NT, ten, gr);
     tpo_shift(pts, NP, gr, ratio, TPO_WARP);
+}
+
+/*
+ * The 1/1.5 window (Tiny::window(w/1.5, h/1.5), software/triangulate/main.cpp:53): the raster has
+ * rw x rh pixels and every fragment fetches the source image at its pixel centre through a
+ * bilinear filter.  The GL driver owns that filter's weight precision, so it is fixed HERE:
+ * float32, one rounding per operation, clamp-to-edge, and the filtered value is truncated to a
+ * byte the way mode 0 truncates int(255*c) (triangle.fs:31-33).  STATED DIVERGENCE: the
+ * reference's mode 1 uses the un-truncated filtered value (triangle.fs:40-42); here both modes see
+ * the truncated texel, so that the energy stays an exact integer function of the raster image.
+ * The CUDA path (k_resample, csrc/table.cuh) evaluates the same expression tree.
+ */
+void tpo_resample(const uint8_t *src, int w, int h, uint8_t *dst, int rw, int rh)
+{
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < rh; j++)
+        for (int i = 0; i < rw; i++) {
+            float fx = (float)i + 0.5f; fx = fx * (float)w; fx = fx / (float)rw; fx = fx - 0.5f;
+            float fy = (float)j + 0.5f; fy = fy * (float)h; fy = fy / (float)rh; fy = fy - 0.5f;
+            const float flx = floorf(fx), fly = floorf(fy);
+            const float ax = fx - flx, ay = fy - fly;
+            const float bx = 1.0f - ax, by = 1.0f - ay;
+            int x0 = (int)flx, y0 = (int)fly;
+            int x1 = x0 + 1 < w - 1 ? x0 + 1 : w - 1, y1 = y0 + 1 < h - 1 ? y0 + 1 : h - 1;
+            if (x0 < 0) x0 = 0; if (y0 < 0) y0 = 0;
+            for (int c = 0; c < 3; c++) {
+                const float p00 = (float)src[4 * ((size_t)y0 * w + x0) + c], p10 = (float)src[4 * ((size_t)y0 * w + x1) + c];
+                const float p01 = (float)src[4 * ((size_t)y1 * w + x0) + c], p11 = (float)src[4 * ((size_t)y1 * w + x1) + c];
+                float top = p00 * bx; { float u = p10 * ax; top = top + u; }
+                float bot = p01 * bx; { float u = p11 * ax; bot = bot + u; }
+                float v = top * by; { float u = bot * ay; v = v + u; }
+                int q = (int)v; if (q < 0) q = 0; if (q > 255) q = 255;
+                dst[4 * ((size_t)j * rw + i) + c] = (uint8_t)q;
+            }
+            dst[4 * ((size_t)j * rw + i) + 3] = 255;
+        }
 }
 
 /* geterr's running sum (source/triangulation.hpp:653-674): float32, index order */

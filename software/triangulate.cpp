@@ -49,6 +49,9 @@ int main(int argc, char* args[])
         const float ratio = tpose::RATIO;
         while (tpose::io::read(&tr, start)) {}                                   // the last record read stays in tr
         tpose::RATIO = ratio;                                                    // io::read overwrote it (io.hpp:81)
+        // io::read leaves `colors` at this level's NT (io.hpp:139-140); the schedule reads MAXT-capacity
+        // colour rows back into it as the mesh grows (triangulate/main.cpp:221-224)
+        tr.colors.resize(tpose::triangulation::MAXT, glm::ivec4(0, 0, 0, 0));
         while (!exportlist.empty() && exportlist.back() <= tr.NT) exportlist.pop_back();
     }
     tpose::upload(&tr, false);

@@ -23,6 +23,8 @@ int main(int argc, char* args[])
     if (!load_image(ia, A)) { std::cout << "Failed to load image A." << std::endl; return 0; }
     if (!load_image(ib, B)) { std::cout << "Failed to load image B." << std::endl; return 0; }
 
+    if (A.w != B.w || A.h != B.h) { std::cout << "Images don't have the same dimension" << std::endl; return 0; }   // warp/main.cpp:51-54
+
     const bool native = has_flag(argc, args, "native");
     // the window is sized from image A for both views (warp/main.cpp:64)
     const int rw = native ? A.w : (int)(A.w / 1.5), rh = native ? A.h : (int)(A.h / 1.5);

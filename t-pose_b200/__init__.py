@@ -45,7 +45,7 @@ EXPORTS = [
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
     "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_carry", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
     "tpose_cuda_mview_last_ms",
-    "tpose_cuda_watch", "tpose_cuda_watch_mask", "tpose_cuda_set_history", "tpose_cuda_history_frame", "tpose_cuda_read", "tpose_cuda_write", "tpose_cuda_batch_step", "tpose_cuda_batch_run",
+    "tpose_cuda_watch", "tpose_cuda_watch_mask", "tpose_cuda_set_history", "tpose_cuda_history_frame", "tpose_cuda_history_restore_gradient", "tpose_cuda_read", "tpose_cuda_write", "tpose_cuda_batch_step", "tpose_cuda_batch_run",
 ]
 
 
@@ -174,6 +174,9 @@ class Context:
         ten = np.empty(self.NT, np.int32); tot = C.c_float()
         self._ck(lib().tpose_cuda_history_frame(self._h, C.c_int(frame), _ptr(pts), _ptr(m), nw, _ptr(ten), C.byref(tot)))
         return dict(pts=pts, mask=np.unpackbits(m.view(np.uint8), bitorder="little")[:self.NT].astype(bool), ten=ten, toterr=tot.value)
+
+    def history_restore_gradient(self, frame):
+        self._ck(lib().tpose_cuda_history_restore_gradient(self._h, C.c_int(frame)))
 
     def read(self, which, first, count):
         dt, width = _BUF_DTYPE[which]

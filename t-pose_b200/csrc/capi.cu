@@ -68,6 +68,7 @@ struct tpose_cuda_ctx {
     // per-frame history of tpose_cuda_run (tpose_cuda_set_history): device arrays + pinned host copies
     int hist_cap = 0, hist_frames = 0, hist_np = 0, hist_nt = 0, hist_np_frames = 0;   // hist_np_frames: frames the last run recorded
     float2* d_hist_pts = nullptr; int* d_hist_ten = nullptr; float* d_hist_err = nullptr; unsigned* d_hist_mask = nullptr;
+    int2* d_hist_gr = nullptr;
     float2* h_hist_pts = nullptr; int* h_hist_ten = nullptr; float* h_hist_err = nullptr; unsigned* h_hist_mask = nullptr;
     unsigned* ticket = nullptr;       // [1] topology trigger accumulator ([0] spare)
     float* err_state = nullptr;       // [0] toterr [1] |relerr| [2] newerr [3] converged flag
@@ -79,6 +80,7 @@ struct tpose_cuda_ctx {
     int* ids = nullptr; size_t ids_cap = 0;
     unsigned char* flush = nullptr; size_t flush_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;   // ev_mid: between k_edges and k_corners of a single step
+    cudaEvent_t ev_batch = nullptr;   // end of the last batch this context led (the other jobs' streams wait on it)
     float last_ms = 0.0f;
     int64_t launches = 0;
     int group = 0;                    // lanes per edge (0 = pick from NT and H)
@@ -206,6 +208,7 @@ extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, 
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     cudaEventCreate(&ctx->ev_mid);
+    cudaEventCreateWithFlags(&ctx->ev_batch, cudaEventDisableTiming);
     {
         const size_t cap = std::max((sizeof(int4) + 3 * sizeof(int)) * (size_t)max_triangles, sizeof(float2) * (size_t)max_points);
         bool ok = cap <= (4u << 20);
@@ -237,7 +240,7 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
     cudaFree(ctx->report); cudaFree(ctx->ids); cudaFree(ctx->flush);
     cudaFree(ctx->job_dev); cudaFree(ctx->batch_jobs);
     if (ctx->h_report) cudaFreeHost(ctx->h_report);
-    cudaFree(ctx->d_hist_pts); cudaFree(ctx->d_hist_ten); cudaFree(ctx->d_hist_err); cudaFree(ctx->d_hist_mask);
+    cudaFree(ctx->d_hist_pts); cudaFree(ctx->d_hist_ten); cudaFree(ctx->d_hist_err); cudaFree(ctx->d_hist_mask); cudaFree(ctx->d_hist_gr);
     if (ctx->h_hist_pts) cudaFreeHost(ctx->h_hist_pts);
     if (ctx->h_hist_ten) cudaFreeHost(ctx->h_hist_ten);
     if (ctx->h_hist_err) cudaFreeHost(ctx->h_hist_err);
@@ -249,6 +252,7 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
+    if (ctx->ev_batch) cudaEventDestroy(ctx->ev_batch);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TPOSE_OK;
@@ -565,6 +569,7 @@ static EvalJob make_job(const tpose_cuda_ctx* ctx, int slot, int flavour)
     j.whe = ctx->watching ? ctx->whe : nullptr;
     j.wmask = ctx->wmask;
     j.hist_pts = ctx->d_hist_pts; j.hist_ten = ctx->d_hist_ten; j.hist_err = ctx->d_hist_err; j.hist_mask = ctx->d_hist_mask;
+    j.hist_gr = ctx->d_hist_gr;
     j.err_state = ctx->err_state; j.run_state = ctx->run_state;
     j.trig = ctx->ticket + 1;
     return j;
@@ -628,7 +633,8 @@ extern "C" int tpose_cuda_energy(tpose_cuda_ctx* ctx, int slot, int flavour)
 {
     int rc = check_ready(ctx, slot, flavour);
     if (rc) return rc;
-    k_zero_gradient<<<(ctx->NP + 255) / 256, 256, 0, ctx->stream>>>(ctx->gr, ctx->NP);   // triangle.vs:95-97
+    if ((rc = rebuild_edges(ctx)) != 0) return rc;                       // corner_off: which vertices are referenced
+    k_zero_gradient<<<(ctx->NP + 255) / 256, 256, 0, ctx->stream>>>(ctx->gr, ctx->NP, ctx->corner_off);   // triangle.vs:95-97
     ctx->launches++;
     const unsigned fl = EV_WRITE_TEN | EV_MEAN_STORED | (flavour == TPOSE_WARP ? 0u : EV_MEAN_DIVIDE);
     return eval(ctx, slot, flavour, ctx->cur, fl);
@@ -754,7 +760,8 @@ extern "C" int tpose_cuda_set_history(tpose_cuda_ctx* ctx, int frames)
     CK(cudaSetDevice(ctx->device));
     if (frames > ctx->hist_cap) {
         CK(cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->d_hist_pts); cudaFree(ctx->d_hist_ten); cudaFree(ctx->d_hist_err); cudaFree(ctx->d_hist_mask);
+        cudaFree(ctx->d_hist_pts); cudaFree(ctx->d_hist_ten); cudaFree(ctx->d_hist_err); cudaFree(ctx->d_hist_mask); cudaFree(ctx->d_hist_gr);
+        ctx->d_hist_gr = nullptr;
         if (ctx->h_hist_pts) cudaFreeHost(ctx->h_hist_pts);
         if (ctx->h_hist_ten) cudaFreeHost(ctx->h_hist_ten);
         if (ctx->h_hist_err) cudaFreeHost(ctx->h_hist_err);
@@ -767,6 +774,7 @@ extern "C" int tpose_cuda_set_history(tpose_cuda_ctx* ctx, int frames)
         CK(cudaMalloc((void**)&ctx->d_hist_ten, sizeof(int) * ctx->maxT * f));
         CK(cudaMalloc((void**)&ctx->d_hist_err, sizeof(float) * f));
         CK(cudaMalloc((void**)&ctx->d_hist_mask, sizeof(unsigned) * words * f));
+        CK(cudaMalloc((void**)&ctx->d_hist_gr, sizeof(int2) * ctx->maxP * f));
         CK(cudaHostAlloc((void**)&ctx->h_hist_pts, sizeof(float2) * ctx->maxP * f, cudaHostAllocDefault));
         CK(cudaHostAlloc((void**)&ctx->h_hist_ten, sizeof(int) * ctx->maxT * f, cudaHostAllocDefault));
         CK(cudaHostAlloc((void**)&ctx->h_hist_err, sizeof(float) * f, cudaHostAllocDefault));
@@ -787,6 +795,19 @@ extern "C" int tpose_cuda_history_frame(tpose_cuda_ctx* ctx, int frame, float* p
     if (ten_base) memcpy(ten_base, ctx->h_hist_ten + (size_t)frame * nt, sizeof(int) * nt);
     if (toterr) *toterr = ctx->h_hist_err[frame];
     if (mask_words) for (int i = 0; i < nwords; i++) mask_words[i] = (size_t)i < words ? ctx->h_hist_mask[(size_t)frame * words + i] : 0u;
+    return TPOSE_OK;
+}
+
+// A caller that rolls the run back to recorded frame `frame` (because its own per-frame code edited
+// the mesh there) must also see pgradbuf as that frame left it: a vertex that the edit leaves without
+// triangles keeps that entry from then on (triangle.vs:93-98 resets referenced vertices only).
+extern "C" int tpose_cuda_history_restore_gradient(tpose_cuda_ctx* ctx, int frame)
+{
+    if (!ctx) return TPOSE_ERR_ARG;
+    if (frame < 0 || frame >= ctx->hist_np_frames) return fail(ctx, TPOSE_ERR_STATE, "history_restore_gradient: the last run recorded no such frame");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->gr, ctx->d_hist_gr + (size_t)frame * ctx->hist_np, sizeof(int2) * (size_t)ctx->hist_np,
+                       cudaMemcpyDeviceToDevice, ctx->stream));
     return TPOSE_OK;
 }
 
@@ -904,6 +925,11 @@ extern "C" int tpose_cuda_batch_step(tpose_cuda_ctx* const* ctxs, int n, const i
     rc = issue_steps(ctx, ctx->batch_jobs, n, shape, fused_flags(flavour), ctx->cur ^ 1, nsteps);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    // the batch ran on the lead context's stream; whatever the caller does next with another job's
+    // context (retrieve, upload, step) goes to that context's own stream and must come after it
+    CK(cudaEventRecord(ctx->ev_batch, ctx->stream));
+    for (int i = 1; i < n; i++)
+        if (ctxs[i]->stream != ctx->stream) CK(cudaStreamWaitEvent(ctxs[i]->stream, ctx->ev_batch, 0));
     for (int i = 0; i < n; i++) ctxs[i]->cur = (ctxs[i]->cur + nsteps) & 1;
     return TPOSE_OK;
 }

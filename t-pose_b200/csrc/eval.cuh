@@ -80,6 +80,7 @@ struct EvalJob {
     int* hist_ten;             // the base energies frame f evaluated (what the reference reads back as terr)
     float* hist_err;           // toterr after frame f's geterr
     unsigned* hist_mask;       // the watch mask at the points frame f left
+    int2* hist_gr;             // pgradbuf as frame f left it (stays on the device; see tpose_cuda_history_restore_gradient)
     float* err_state;          // [0] toterr [1] |relerr| [2] newerr [3] converged flag of the last check
     int* run_state;            // RS_*
     unsigned* trig;            // [0] topology trigger accumulator
@@ -503,20 +504,27 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame)
         gx = __reduce_add_sync(0xffffffffu, gx);
         gy = __reduce_add_sync(0xffffffffu, gy);
         if (lane == 0 && !stop) {
-            // shift.cs:16-47 (vertices nothing references get a zero gradient and are still clamped)
-            J.gr[v] = make_int2((int)gx, (int)gy);
+            // A vertex no triangle references is never zeroed by the vertex stage (triangle.vs:93-98 resets
+            // gr only for the three vertices of each instance) and gradient.cs adds nothing to it: its
+            // entry stays what an earlier frame left there, and shift.cs:16-47 goes on applying it.
+            if (c0 == c1) { const int2 stale = J.gr[v]; gx = (unsigned)stale.x; gy = (unsigned)stale.y; }
+            else J.gr[v] = make_int2((int)gx, (int)gy);
             if (v >= 4) { p = shift_vertex(p, (int)gx, (int)gy, J.ratio, J.step); J.pts[v] = p; }
-            if ((flags & EV_HISTORY) && frame >= 0) J.hist_pts[(size_t)frame * J.NP + v] = p;
+            if ((flags & EV_HISTORY) && frame >= 0) {
+                J.hist_pts[(size_t)frame * J.NP + v] = p;
+                J.hist_gr[(size_t)frame * J.NP + v] = make_int2((int)gx, (int)gy);
+            }
         }
     }
     TL(1, 4);
 }
 
 // un-fused gradient.cs / shift.cs, for the literal doshift() entry point
-__global__ void k_zero_gradient(int2* gr, int np)
+// triangle.vs:93-98: only vertices some triangle references are reset
+__global__ void k_zero_gradient(int2* gr, int np, const int* __restrict__ corner_off)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < np) gr[v] = make_int2(0, 0);
+    if (v < np && corner_off[v + 1] > corner_off[v]) gr[v] = make_int2(0, 0);
 }
 
 __global__ void k_gradient(const int4* __restrict__ tri, int nt, const int* __restrict__ ten, int2* gr)

@@ -128,6 +128,23 @@ def test_ported_programs_write_the_same_files_as_the_library_calls(dev, synth, t
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "levels" in out.stdout, out.stdout + out.stderr
     assert os.path.getsize(paths[0] + ".tri.warp") == os.path.getsize(paths[0] + ".tri")
+    # extension -t: continue from the finest level of an existing stack.  io::read leaves `colors` at that
+    # level's NT; every level exported afterwards must still carry mean colours (bytes), not raw sums.
+    import shutil, struct
+    start = str(tmp_path / "start.tri")
+    shutil.copy(paths[0] + ".tri", start)
+    cont = str(tmp_path / "cont.ppm")
+    shutil.copy(paths[0], cont)
+    out = subprocess.run([exe_t, "-i", cont, "-native", "-t", start, "-frames", "8000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "steps/s" in out.stdout, out.stdout + out.stderr
+    buf, o, nrec = open(cont + ".tri", "rb").read(), 0, 0
+    while o < len(buf):
+        _, nt = struct.unpack_from("<fi", buf, o); o += 8
+        rec = np.frombuffer(buf, np.int32, 9 * nt, o).reshape(nt, 9); o += 36 * nt
+        (npnt,) = struct.unpack_from("<i", buf, o); o += 4 + 16 * npnt
+        assert rec[:, 6:9].min() >= 0 and rec[:, 6:9].max() <= 255, "exported colours are not means"
+        nrec += 1
+    assert nrec >= 1, "the continuation exported no level: lengthen -frames"
     # software/view, headless: one picture per level
     exe_v = os.path.join(root, "t-pose_b200", "bin", "view")
     out = subprocess.run([exe_v, "-t", paths[0] + ".tri", "-o", str(tmp_path / "shot"), "-height", "120"], capture_output=True, text=True, timeout=300)

@@ -136,37 +136,6 @@ def test_raster_ids_match_oracle(cuda_pkg, synth, O):
     ctx.close()
 
 
-def test_full_size_properties_1080p(cuda_pkg, synth):
-    """BASELINE size (1920x1080, 3000 triangles): size-independent properties instead of the oracle."""
-    w, h = 1920, 1080
-    ratio = w / h
-    img = synth.make_image(w, h, seed=1000)
-    pts, tri, _ = synth.mesh_for(3000, ratio)
-    NT = tri.shape[0]
-    ctx = _ctx(cuda_pkg)
-    ctx.set_image(0, img)
-    ctx.upload(pts, tri, ratio)
-    ctx.step(0, cuda_pkg.TRIANGULATE, 1)
-    got = ctx.retrieve()
-    # the base triangles tile the window: counts and colour sums are checksums of the image
-    assert int(got["cn"][:NT].sum()) == w * h
-    assert np.array_equal(got["ca"][:NT, :3].astype(np.int64).sum(0), img[..., :3].reshape(-1, 3).astype(np.int64).sum(0))
-    # determinism / idempotence of evaluation: same positions -> same rows
-    ctx.upload(pts, tri, ratio)
-    ctx.step(0, cuda_pkg.TRIANGULATE, 1)
-    again = ctx.retrieve()
-    for k in ("cn", "ca", "ten"):
-        assert np.array_equal(got[k], again[k])
-    assert np.array_equal(bits(got["pts"]), bits(again["pts"]))
-    # corners never move (shift.cs:20)
-    assert np.array_equal(bits(got["pts"][:4]), bits(pts[:4]))
-    # ids raster agrees with the counts
-    ctx.upload(pts, tri, ratio)
-    ids = ctx.raster_ids(0)
-    assert np.array_equal(np.bincount(ids.ravel(), minlength=NT), got["cn"][:NT])
-    ctx.close()
-
-
 def test_run_stops_on_convergence_like_geterr(cuda_pkg, synth, O):
     """tpose_cuda_run == stepping one frame at a time and applying geterr on the host."""
     w, h = 256, 160
