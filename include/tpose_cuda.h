@@ -237,6 +237,12 @@ int tpose_cuda_last_elapsed_ms(tpose_cuda_ctx *ctx, float *ms);
  * per-variant evaluation + vertex update (k_corners).  TPOSE_ERR_STATE after any other call. */
 int tpose_cuda_set_kernel_timing(tpose_cuda_ctx *ctx, int on);
 int tpose_cuda_last_kernel_ms(tpose_cuda_ctx *ctx, float *edges_ms, float *corners_ms);
+/* Which kernels integrate the edges: 0 = gathers from a row-prefix table (k_edges, the default), 1 = TMA-staged
+ * image tiles (k_setup + k_tiles; environment TPOSE_CUDA_PATH=tiles when the context is created).  On the
+ * tile path edges_ms above is k_tiles alone and tpose_cuda_last_setup_ms is the k_setup in front of it
+ * (snapped end points, tile ranges, zeroed records); both produce identical records. */
+int tpose_cuda_kernel_path(const tpose_cuda_ctx *ctx);
+int tpose_cuda_last_setup_ms(tpose_cuda_ctx *ctx, float *setup_ms);
 /* Block until the context's stream is idle. */
 int tpose_cuda_sync(tpose_cuda_ctx *ctx);
 /* Number of kernel launches issued by this context so far. */

@@ -41,7 +41,7 @@ EXPORTS = [
     "tpose_cuda_upload_points", "tpose_cuda_colors", "tpose_cuda_energy", "tpose_cuda_shift",
     "tpose_cuda_step", "tpose_cuda_frame", "tpose_cuda_run", "tpose_cuda_set_toterr", "tpose_cuda_get_toterr",
     "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
-    "tpose_cuda_raster_ids", "tpose_cuda_render", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_set_kernel_timing", "tpose_cuda_set_step_scale", "tpose_cuda_sync",
+    "tpose_cuda_raster_ids", "tpose_cuda_render", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_last_setup_ms", "tpose_cuda_kernel_path", "tpose_cuda_set_kernel_timing", "tpose_cuda_set_step_scale", "tpose_cuda_sync",
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
     "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_carry", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
     "tpose_cuda_mview_last_ms",
@@ -252,6 +252,15 @@ class Context:
         a, b = C.c_float(), C.c_float()
         self._ck(lib().tpose_cuda_last_kernel_ms(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def last_setup_ms(self):
+        a = C.c_float()
+        self._ck(lib().tpose_cuda_last_setup_ms(self._h, C.byref(a)))
+        return a.value
+
+    def kernel_path(self):
+        """'tiles' (TMA-staged image tiles) or 'table' (row-prefix table gathers, TPOSE_CUDA_PATH=table)."""
+        return "tiles" if lib().tpose_cuda_kernel_path(self._h) == 1 else "table"
 
     def sync(self):
         self._ck(lib().tpose_cuda_sync(self._h))

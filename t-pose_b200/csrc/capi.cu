@@ -7,6 +7,9 @@
 #include "mview.cuh"
 #include "raster.cuh"
 #include "table.cuh"
+#include "tiles.cuh"
+
+#include <cuda.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -20,16 +23,22 @@ using namespace tpose_dev;
 
 // Launch geometry of one evaluation.  Grid sizes are quantised (power of two, at most one full
 // wave) and the kernels stride, so a captured sequence stays valid while the mesh grows.
-struct EvalShape { int group, grid_e, grid_t; bool narrow; };
+// path: 0 = row-prefix table gathers (k_edges), 1 = TMA-staged tiles (k_setup + k_tiles)
+struct EvalShape { int group, grid_e, grid_t; bool narrow; int path, grid_s, grid_tiles; };
+constexpr int kPathTable = 0, kPathTiles = 1;
+constexpr int kTileH = 64;
 // a sequence of evaluations (see issue_sequence) and its instantiated graph
 struct SeqKey { const EvalJob* jobs; int njobs; EvalShape shape; int kind, len, first_set; unsigned flags; double tol; };
 struct SeqGraph { SeqKey key; cudaGraphExec_t exec; uint64_t stamp; };
 
 struct ImageSlot {
-    uchar4* rgba = nullptr;    // raster-resolution image on the device
-    uint4* table = nullptr;    // row-prefix moments, (W+1) entries per row
-    int W = 0, H = 0, pitch = 0;
-    size_t rgba_cap = 0, table_cap = 0;
+    uchar4* rgba = nullptr;    // raster-resolution image on the device, rows ipitch pixels apart
+    uint4* table = nullptr;    // table path: row-prefix moments, (W+1) entries per row
+    uint4* coarse = nullptr;   // tile path: prefix at every tile column's left border, [ntx+1][H]
+    void* tmap = nullptr;      // tile path: CUtensorMap of rgba in device memory (128 bytes)
+    int W = 0, H = 0, pitch = 0, ipitch = 0, ntx = 0, nty = 0;
+    size_t rgba_cap = 0, table_cap = 0, coarse_cap = 0;
+    bool ready = false;
 };
 
 struct tpose_cuda_ctx {
@@ -56,6 +65,8 @@ struct tpose_cuda_ctx {
     std::vector<int32_t> tri_host;    // mirror of the index buffer, 4 ints per triangle
     int2* edges = nullptr; int4* tri_edges = nullptr; int* corner_off = nullptr; int* corners = nullptr;
     EdgeRec* rec = nullptr;
+    int2* esnap = nullptr; unsigned* ebox = nullptr; unsigned* gbox = nullptr;   // tile path, per step
+    int path = kPathTable;            // measured faster on B200; TPOSE_CUDA_PATH=tiles selects the TMA tiles
     int NE = 0, edges_np = 0;
     bool edges_dirty = true;
     std::vector<uint64_t> scratch_keys; tpose::edgeview::view edge_view;
@@ -79,7 +90,8 @@ struct tpose_cuda_ctx {
     EvalJob* batch_jobs = nullptr; int batch_cap = 0;   // job array when this context leads a batch
     int* ids = nullptr; size_t ids_cap = 0;
     unsigned char* flush = nullptr; size_t flush_cap = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;   // ev_mid: between k_edges and k_corners of a single step
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;   // ev_mid: between k_edges / k_tiles and k_corners of a single step
+    cudaEvent_t ev_mid0 = nullptr;    // tile path: between k_setup and k_tiles
     cudaEvent_t ev_batch = nullptr;   // end of the last batch this context led (the other jobs' streams wait on it)
     float last_ms = 0.0f;
     int64_t launches = 0;
@@ -133,7 +145,7 @@ static int upload_bytes(tpose_cuda_ctx* ctx, void* dst, const void* src, size_t 
 
 extern "C" const char* tpose_cuda_version(void)
 {
-    return "tpose-cuda 0.2 (sm_100a; shared-edge integrals over row-prefix moment tables)";
+    return "tpose-cuda 0.3 (sm_100a; shared-edge integrals over row-prefix moment tables or TMA-staged image tiles)";
 }
 
 extern "C" const char* tpose_cuda_last_error(const tpose_cuda_ctx* ctx)
@@ -192,6 +204,9 @@ extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, 
     ALLOC(ctx->corner_off, sizeof(int) * ((size_t)max_points + 1));
     ALLOC(ctx->corners, sizeof(int) * 3 * (size_t)max_triangles);
     ALLOC(ctx->rec, sizeof(EdgeRec) * kEdgeMoves * 3 * (size_t)max_triangles);
+    ALLOC(ctx->esnap, sizeof(int2) * kSnapPerEdge * 3 * (size_t)max_triangles);
+    ALLOC(ctx->ebox, sizeof(unsigned) * 3 * (size_t)max_triangles);
+    ALLOC(ctx->gbox, sizeof(unsigned) * ((3 * (size_t)max_triangles + kEdgeGroup - 1) / kEdgeGroup + 1));
     ALLOC(ctx->ticket, sizeof(unsigned) * 2);
     ALLOC(ctx->job_dev, sizeof(EvalJob));
 #undef ALLOC
@@ -208,6 +223,7 @@ extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, 
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     cudaEventCreate(&ctx->ev_mid);
+    cudaEventCreate(&ctx->ev_mid0);
     cudaEventCreateWithFlags(&ctx->ev_batch, cudaEventDisableTiming);
     {
         const size_t cap = std::max((sizeof(int4) + 3 * sizeof(int)) * (size_t)max_triangles, sizeof(float2) * (size_t)max_points);
@@ -220,6 +236,14 @@ extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, 
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail("init", e);
     const char* g = getenv("TPOSE_CUDA_GROUP");
     if (g) ctx->group = atoi(g);
+    // TPOSE_CUDA_PATH = table | tiles: which kernels integrate the edges (both produce the same records, bit for bit)
+    const char* pth = getenv("TPOSE_CUDA_PATH");
+    if (pth && std::string(pth) == "table") ctx->path = kPathTable;
+    else if (pth && std::string(pth) == "tiles") ctx->path = kPathTiles;
+    if (ctx->path == kPathTiles) {
+        cudaError_t ea = cudaFuncSetAttribute(k_tiles<kTileH>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_bytes<kTileH>());
+        if (ea != cudaSuccess) return bail("k_tiles shared memory", ea);
+    }
     const char* ng = getenv("TPOSE_CUDA_NO_GRAPH");
     if (ng && atoi(ng)) ctx->use_graphs = false;
     *out = ctx;
@@ -232,7 +256,8 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
-    for (auto& s : ctx->img) { cudaFree(s.rgba); cudaFree(s.table); }
+    for (auto& s : ctx->img) { cudaFree(s.rgba); cudaFree(s.table); cudaFree(s.coarse); cudaFree(s.tmap); }
+    cudaFree(ctx->esnap); cudaFree(ctx->ebox); cudaFree(ctx->gbox);
     for (int s = 0; s < 2; s++) { cudaFree(ctx->cn[s]); cudaFree(ctx->ca[s]); cudaFree(ctx->ten[s]); }
     cudaFree(ctx->staging); cudaFree(ctx->tri);
     cudaFree(ctx->edges); cudaFree(ctx->tri_edges); cudaFree(ctx->corner_off); cudaFree(ctx->corners); cudaFree(ctx->rec);
@@ -252,6 +277,7 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
+    if (ctx->ev_mid0) cudaEventDestroy(ctx->ev_mid0);
     if (ctx->ev_batch) cudaEventDestroy(ctx->ev_batch);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -262,17 +288,58 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
 
 static int build_table(tpose_cuda_ctx* ctx, ImageSlot& s)
 {
-    const bool bulk = (s.W % 4 == 0);
-    const size_t smem = bulk ? (size_t)s.W * 4 : 0;
-    if (bulk) {
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_build_table<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_build_table<true><<<s.H, kTableThreads, smem, ctx->stream>>>(s.rgba, s.W, s.H, s.table, s.pitch);
-    } else {
-        k_build_table<false><<<s.H, kTableThreads, 0, ctx->stream>>>(s.rgba, s.W, s.H, s.table, s.pitch);
-    }
+    const size_t need_table = (size_t)(s.W + 1) * s.H * sizeof(uint4);
+    if (s.table_cap < need_table) { cudaFree(s.table); s.table = nullptr; CK(cudaMalloc((void**)&s.table, need_table)); s.table_cap = need_table; }
+    s.pitch = s.W + 1;
+    const size_t smem = (size_t)s.ipitch * 4;
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_build_table<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_build_table<true><<<s.H, kTableThreads, smem, ctx->stream>>>(s.rgba, s.ipitch, s.W, s.H, s.table, s.pitch);
     ctx->launches++;
     CK(cudaGetLastError());
     return TPOSE_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// tile path: coarse column prefixes + the tensor map the tiles are loaded through
+static int build_tiles(tpose_cuda_ctx* ctx, ImageSlot& s)
+{
+    s.ntx = (s.W + kTileW - 1) / kTileW;
+    s.nty = (s.H + kTileH - 1) / kTileH;
+    const size_t need = (size_t)(s.ntx + 1) * s.H * sizeof(uint4);
+    if (s.coarse_cap < need) { cudaFree(s.coarse); s.coarse = nullptr; CK(cudaMalloc((void**)&s.coarse, need)); s.coarse_cap = need; }
+    if (!s.tmap) CK(cudaMalloc(&s.tmap, sizeof(CUtensorMap)));
+    k_build_coarse<<<s.H, kTableThreads, 0, ctx->stream>>>(s.rgba, s.ipitch, s.W, s.H, s.coarse, s.ntx);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(ctx, TPOSE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver (TPOSE_CUDA_PATH=table selects the table kernels)");
+    alignas(64) CUtensorMap tm;
+    const cuuint64_t gdim[2] = {(cuuint64_t)s.W, (cuuint64_t)s.H};
+    const cuuint64_t gstride[1] = {(cuuint64_t)s.ipitch * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kTileW, (cuuint32_t)kTileH};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, s.rgba, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, TPOSE_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    return upload_bytes(ctx, s.tmap, &tm, sizeof tm);
 }
 
 static int set_image_common(tpose_cuda_ctx* ctx, int slot, const uint8_t* src, bool src_on_host,
@@ -285,24 +352,29 @@ static int set_image_common(tpose_cuda_ctx* ctx, int slot, const uint8_t* src, b
         return fail(ctx, TPOSE_ERR_CAPACITY, "set_image: raster exceeds 4095 x 8192");
     CK(cudaSetDevice(ctx->device));
     ImageSlot& s = ctx->img[slot];
-    const size_t need_rgba = (size_t)rw * rh * sizeof(uchar4);
-    const size_t need_table = (size_t)(rw + 1) * rh * sizeof(uint4);
+    s.ready = false;
+    const int ipitch = (rw + 3) & ~3;                 // rows start 16-byte aligned (bulk copies, the tensor map's stride)
+    const size_t need_rgba = (size_t)ipitch * rh * sizeof(uchar4);
     if (s.rgba_cap < need_rgba) { cudaFree(s.rgba); s.rgba = nullptr; CK(cudaMalloc((void**)&s.rgba, need_rgba)); s.rgba_cap = need_rgba; }
-    if (s.table_cap < need_table) { cudaFree(s.table); s.table = nullptr; CK(cudaMalloc((void**)&s.table, need_table)); s.table_cap = need_table; }
-    s.W = rw; s.H = rh; s.pitch = rw + 1;
+    s.W = rw; s.H = rh; s.ipitch = ipitch;
     const cudaMemcpyKind kind = src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (ipitch != rw) CK(cudaMemsetAsync(s.rgba, 0, need_rgba, ctx->stream));
     if (rw == w && rh == h) {
-        CK(cudaMemcpyAsync(s.rgba, src, need_rgba, kind, ctx->stream));
+        if (ipitch == rw) CK(cudaMemcpyAsync(s.rgba, src, need_rgba, kind, ctx->stream));
+        else CK(cudaMemcpy2DAsync(s.rgba, (size_t)ipitch * 4, src, (size_t)w * 4, (size_t)w * 4, (size_t)h, kind, ctx->stream));
     } else {
         const size_t need_src = (size_t)w * h * sizeof(uchar4);
         if (ctx->staging_cap < need_src) { cudaFree(ctx->staging); ctx->staging = nullptr; CK(cudaMalloc((void**)&ctx->staging, need_src)); ctx->staging_cap = need_src; }
         CK(cudaMemcpyAsync(ctx->staging, src, need_src, kind, ctx->stream));
         dim3 grid((rw + 127) / 128, rh);
-        k_resample<<<grid, 128, 0, ctx->stream>>>(ctx->staging, w, h, s.rgba, rw, rh);
+        k_resample<<<grid, 128, 0, ctx->stream>>>(ctx->staging, w, h, s.rgba, ipitch, rw, rh);
         ctx->launches++;
         CK(cudaGetLastError());
     }
-    return build_table(ctx, s);
+    const int rc = ctx->path == kPathTiles ? build_tiles(ctx, s) : build_table(ctx, s);
+    if (rc) return rc;
+    s.ready = true;
+    return TPOSE_OK;
 }
 
 extern "C" int tpose_cuda_set_image(tpose_cuda_ctx* ctx, int slot, const uint8_t* rgba_host, int w, int h, int rw, int rh)
@@ -426,11 +498,18 @@ static int quantised_grid(long long blocks_needed)
     return g < kMaxGridBlocks ? g : kMaxGridBlocks;
 }
 
-static EvalShape make_shape(int group, int max_np, int max_ne, bool narrow)
+static EvalShape make_shape(int group, int max_np, int max_ne, bool narrow, int path, int max_tiles)
 {
     const int per_block = kEdgeThreads / group;
-    return EvalShape{group, quantised_grid(((long long)max_ne * kEdgeMoves + per_block - 1) / per_block),
-                     quantised_grid((max_np + kCornerWarps - 1) / kCornerWarps), narrow};
+    EvalShape sh{group, quantised_grid(((long long)max_ne * kEdgeMoves + per_block - 1) / per_block),
+                 quantised_grid((max_np + kCornerWarps - 1) / kCornerWarps), narrow, path, 0, 0};
+    if (path == kPathTiles) {
+        // (group, grid_e and narrow do not exist on the tile path: keep them out of the graph key)
+        sh.group = 1; sh.grid_e = 0; sh.narrow = true;
+        sh.grid_s = quantised_grid((max_ne + kSetupThreads - 1) / kSetupThreads);
+        sh.grid_tiles = max_tiles;
+    }
+    return sh;
 }
 
 template <int G>
@@ -441,10 +520,18 @@ static void launch_edges(const EvalJob* jobs, int njobs, const EvalShape& sh, in
     else k_edges<G, unsigned long long><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame);
 }
 
-// one evaluation of every job: k_edges then k_corners
+// one evaluation of every job: k_edges (or k_setup + k_tiles) then k_corners
 static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int set, unsigned flags, double tol, int frame, cudaStream_t st,
-                        cudaEvent_t mid = nullptr)
+                        cudaEvent_t mid = nullptr, cudaEvent_t mid0 = nullptr)
 {
+    if (sh.path == kPathTiles) {
+        k_setup<kTileH><<<dim3(sh.grid_s + 1, njobs), kSetupThreads, 0, st>>>(jobs, set, flags, tol, frame);   // + the service block
+        if (mid0) cudaEventRecord(mid0, st);
+        k_tiles<kTileH><<<dim3(sh.grid_tiles, njobs), kTileThreads, tile_smem_bytes<kTileH>(), st>>>(jobs, flags);
+        if (mid) cudaEventRecord(mid, st);
+        k_corners<<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame);
+        return;
+    }
     switch (sh.group) {
     case 1: launch_edges<1>(jobs, njobs, sh, set, flags, tol, frame, st); break;
     case 2: launch_edges<2>(jobs, njobs, sh, set, flags, tol, frame, st); break;
@@ -456,7 +543,7 @@ static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int
     if (mid) cudaEventRecord(mid, st);
     k_corners<<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame);
 }
-constexpr int kLaunchesPerEval = 2;
+static int launches_per_eval(const EvalShape& sh) { return sh.path == kPathTiles ? 3 : 2; }
 
 // ---- sequences of evaluations, replayed as CUDA graphs ------------------------------------------
 // A sequence is `len` evaluations into alternating buffer sets starting at `first_set`.
@@ -468,7 +555,7 @@ constexpr int kLaunchesPerEval = 2;
 constexpr int kGraphMinLen = 1;
 constexpr size_t kGraphCacheSize = 64;
 
-static void issue_direct(const SeqKey& k, cudaStream_t st, cudaEvent_t mid = nullptr)
+static void issue_direct(const SeqKey& k, cudaStream_t st, cudaEvent_t mid = nullptr, cudaEvent_t mid0 = nullptr)
 {
     for (int j = 0; j < k.len; j++) {
         unsigned f = k.flags;
@@ -476,7 +563,7 @@ static void issue_direct(const SeqKey& k, cudaStream_t st, cudaEvent_t mid = nul
             if (j > 0) f |= EV_CHECK_PREV;
             if (j == k.len - 1) f |= EV_FINAL;
         }
-        launch_eval(k.shape, k.jobs, k.njobs, (k.first_set + j) & 1, f, k.tol, k.kind == 1 ? j : -1, st, mid);
+        launch_eval(k.shape, k.jobs, k.njobs, (k.first_set + j) & 1, f, k.tol, k.kind == 1 ? j : -1, st, mid, mid0);
     }
 }
 
@@ -484,16 +571,17 @@ static bool same_key(const SeqKey& a, const SeqKey& b)
 {
     return a.jobs == b.jobs && a.njobs == b.njobs && a.kind == b.kind && a.len == b.len && a.first_set == b.first_set &&
            a.flags == b.flags && a.tol == b.tol && a.shape.group == b.shape.group && a.shape.grid_e == b.shape.grid_e &&
-           a.shape.grid_t == b.shape.grid_t && a.shape.narrow == b.shape.narrow;
+           a.shape.grid_t == b.shape.grid_t && a.shape.narrow == b.shape.narrow && a.shape.path == b.shape.path &&
+           a.shape.grid_s == b.shape.grid_s && a.shape.grid_tiles == b.shape.grid_tiles;
 }
 
 static int issue_sequence(tpose_cuda_ctx* ctx, const SeqKey& key)
 {
     ctx->run_cache_valid = false; ctx->run_mask_valid = false;
-    ctx->launches += (int64_t)kLaunchesPerEval * key.len;
+    ctx->launches += (int64_t)launches_per_eval(key.shape) * key.len;
     if (key.len < kGraphMinLen || !ctx->use_graphs || (key.len == 1 && ctx->time_kernels)) {
         const bool mid = key.len == 1 && ctx->time_kernels;
-        issue_direct(key, ctx->stream, mid ? ctx->ev_mid : nullptr);
+        issue_direct(key, ctx->stream, mid ? ctx->ev_mid : nullptr, mid ? ctx->ev_mid0 : nullptr);
         ctx->mid_valid = mid;
         CK(cudaGetLastError());
         return TPOSE_OK;
@@ -557,6 +645,8 @@ static EvalJob make_job(const tpose_cuda_ctx* ctx, int slot, int flavour)
     EvalJob j;
     memset(&j, 0, sizeof j);
     j.table = s.table; j.pitch = s.pitch; j.W = s.W; j.H = s.H;
+    j.tmap = s.tmap; j.coarse = s.coarse; j.ntx = s.ntx; j.nty = s.nty;
+    j.esnap = ctx->esnap; j.ebox = ctx->ebox; j.gbox = ctx->gbox;
     j.pts = ctx->pts; j.tri = ctx->tri; j.NT = ctx->NT; j.NP = ctx->NP; j.NE = ctx->NE;
     j.edges = ctx->edges; j.tri_edges = ctx->tri_edges; j.corner_off = ctx->corner_off; j.corners = ctx->corners;
     j.rec = ctx->rec;
@@ -592,7 +682,7 @@ static int sync_job(tpose_cuda_ctx* ctx, int slot, int flavour)
 static EvalShape shape_of(const tpose_cuda_ctx* ctx, int slot)
 {
     const ImageSlot& im = ctx->img[slot];
-    return make_shape(pick_group(ctx, ctx->NT, im.H), ctx->NP, ctx->NE, narrow_sums(im.W, im.H));
+    return make_shape(pick_group(ctx, ctx->NT, im.H), ctx->NP, ctx->NE, narrow_sums(im.W, im.H), ctx->path, im.ntx * im.nty);
 }
 
 static int eval(tpose_cuda_ctx* ctx, int slot, int flavour, int set, unsigned flags, double tol = 0.0)
@@ -609,7 +699,7 @@ static int check_ready(tpose_cuda_ctx* ctx, int slot, int flavour)
     if (!ctx) return TPOSE_ERR_ARG;
     if (slot < 0 || slot > 1 || (flavour != TPOSE_TRIANGULATE && flavour != TPOSE_WARP)) return fail(ctx, TPOSE_ERR_ARG, "bad slot or flavour");
     if (!ctx->have_mesh) return fail(ctx, TPOSE_ERR_STATE, "no mesh uploaded");
-    if (!ctx->img[slot].table) return fail(ctx, TPOSE_ERR_STATE, "no image in this slot");
+    if (!ctx->img[slot].ready) return fail(ctx, TPOSE_ERR_STATE, "no image in this slot");
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return fail(ctx, TPOSE_ERR_CUDA, cudaGetErrorString(e));
     return TPOSE_OK;
@@ -884,12 +974,13 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
     tpose_cuda_ctx* lead = ctxs[0];
     tpose_cuda_ctx* ctx = lead;   // for CK
     std::vector<EvalJob> jobs((size_t)n);
-    int mxp = 0, mxe = 0; double rows = 0.0, items = 0.0; bool narrow = true;
+    int mxp = 0, mxe = 0, mxt = 0; double rows = 0.0, items = 0.0; bool narrow = true;
     for (int i = 0; i < n; i++) {
         const int slot = slots ? slots[i] : 0;
         int rc = check_ready(ctxs[i], slot, flavour);
         if (rc) { if (ctxs[i] && ctxs[i] != lead) lead->err = "batch: job " + std::to_string(i) + ": " + ctxs[i]->err; return rc; }
         if (ctxs[i]->device != lead->device) return fail(lead, TPOSE_ERR_ARG, "batch: contexts live on different devices");
+        if (ctxs[i]->path != lead->path) return fail(lead, TPOSE_ERR_ARG, "batch: contexts use different kernel paths");
         for (int k = 0; k < i; k++) if (ctxs[k] == ctxs[i]) return fail(lead, TPOSE_ERR_ARG, "batch: a context appears twice");
         if (ctxs[i] != lead) cudaStreamSynchronize(ctxs[i]->stream);   // its uploads are done before we touch its buffers
         ctxs[i]->run_cache_valid = false;
@@ -899,6 +990,7 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
         jobs[(size_t)i].flip = ctxs[i]->cur ^ lead->cur;   // contexts need not have done the same number of steps
         mxp = ctxs[i]->NP > mxp ? ctxs[i]->NP : mxp;
         mxe = ctxs[i]->NE > mxe ? ctxs[i]->NE : mxe;
+        mxt = std::max(mxt, ctxs[i]->img[slot].ntx * ctxs[i]->img[slot].nty);
         items += (double)ctxs[i]->NE * kEdgeMoves;
         narrow = narrow && narrow_sums(ctxs[i]->img[slot].W, ctxs[i]->img[slot].H);
         rows += mean_edge_rows(ctxs[i]->NT, ctxs[i]->img[slot].H);
@@ -910,7 +1002,7 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
     }
     CK(cudaMemcpyAsync(lead->batch_jobs, jobs.data(), sizeof(EvalJob) * n, cudaMemcpyHostToDevice, lead->stream));
     CK(cudaStreamSynchronize(lead->stream));   // `jobs` is a local
-    *shape = make_shape(valid_group(lead->group) ? lead->group : group_for(rows / n, items), mxp, mxe, narrow);
+    *shape = make_shape(valid_group(lead->group) ? lead->group : group_for(rows / n, items), mxp, mxe, narrow, lead->path, mxt);
     return TPOSE_OK;
 }
 
@@ -1140,10 +1232,25 @@ extern "C" int tpose_cuda_last_kernel_ms(tpose_cuda_ctx* ctx, float* edges_ms, f
     if (!ctx->mid_valid) return fail(ctx, TPOSE_ERR_STATE, "last_kernel_ms: needs tpose_cuda_set_kernel_timing(ctx, 1) and a single tpose_cuda_step(.., 1) as the last call");
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventSynchronize(ctx->ev1));
-    CK(cudaEventElapsedTime(edges_ms, ctx->ev0, ctx->ev_mid));
+    CK(cudaEventElapsedTime(edges_ms, ctx->path == kPathTiles ? ctx->ev_mid0 : ctx->ev0, ctx->ev_mid));   // k_edges, or k_tiles alone
     CK(cudaEventElapsedTime(corners_ms, ctx->ev_mid, ctx->ev1));
     return TPOSE_OK;
 }
+
+// tile path: the step's first kernel (k_setup: snapped end points, tile ranges, zeroed records); 0 on the table path
+extern "C" int tpose_cuda_last_setup_ms(tpose_cuda_ctx* ctx, float* setup_ms)
+{
+    if (!ctx || !setup_ms) return TPOSE_ERR_ARG;
+    if (!ctx->mid_valid) return fail(ctx, TPOSE_ERR_STATE, "last_setup_ms: needs tpose_cuda_set_kernel_timing(ctx, 1) and a single tpose_cuda_step(.., 1) as the last call");
+    *setup_ms = 0.0f;
+    if (ctx->path != kPathTiles) return TPOSE_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(setup_ms, ctx->ev0, ctx->ev_mid0));
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_kernel_path(const tpose_cuda_ctx* ctx) { return ctx ? ctx->path : -1; }
 
 #ifdef TPOSE_TIMELINE
 // development aid: out[2][6][8192] globaltimer stamps (ns) per warp; reset != 0 zeroes them

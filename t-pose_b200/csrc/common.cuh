@@ -114,6 +114,41 @@ struct EdgeWalk {
         if (tr < 0) { tr += dy; --dq; }
         dr = 256ll * tr;
     }
+    // The rows of the edge that fall inside [row_lo, row_hi) (a tile), stride 1: the same state as
+    // init() followed by next() up to the first of those rows.
+    __device__ __forceinline__ void init_rows(int2 a, int2 b, int row_lo, int row_hi)
+    {
+        sign = (b.y > a.y) - (b.y < a.y);
+        if (a.y > b.y) { int2 t = a; a = b; b = t; }
+        const int lo = a.y, hi = b.y;
+        const int r0 = max((lo - 128 + 255) >> 8, row_lo);
+        r_end = min((hi - 128 + 255) >> 8, row_hi);
+        r = r0;
+        q = 0; dq = 0; rem = 0; den = 1; dr = 0;
+        if (sign == 0 || r >= r_end) { r = r_end; return; }
+        const int dy = hi - lo, dx = b.x - a.x;
+        const int m = 256 * r + 128 - lo;             // 0 <= m < dy
+        int w, wr;
+        const unsigned adx = (unsigned)abs(dx);
+        if (__umulhi(adx, (unsigned)m) == 0 && adx * (unsigned)m < 0x7fffffffu) {
+            const int z = dx * m - 1;
+            w = z / dy; wr = z - w * dy;
+            if (wr < 0) { wr += dy; --w; }
+        } else {
+            const long long z = (long long)dx * m - 1;
+            long long w64 = z / dy, wr64 = z - w64 * dy;
+            if (wr64 < 0) { wr64 += dy; --w64; }
+            w = (int)w64; wr = (int)wr64;
+        }
+        const int s = a.x + 128 + w;
+        q = s >> 8;
+        den = 256ll * dy;
+        rem = (long long)(s & 255) * dy + wr;
+        dq = dx / dy;
+        int tr = dx - dq * dy;
+        if (tr < 0) { tr += dy; --dq; }
+        dr = 256ll * tr;
+    }
     __device__ __forceinline__ bool done() const { return r >= r_end; }
     __device__ __forceinline__ int cross(int W) const { return min(max(q, 0), W); }
     __device__ __forceinline__ void next(int stride)

@@ -50,9 +50,10 @@ enum { RS_STOP = 0, RS_STEPS = 1, RS_TRIG = 2, RS_SPARE = 3 };
 constexpr int kEdgeMoves = 9;        // per unique edge: as it is + 4 moves of each end point
 
 // signed integral of one (edge, move) item, in the direction first -> second end point
+// (six 64-bit words: the tile path adds partial records into it with 64-bit bulk reductions)
 struct __align__(16) EdgeRec {
     long long r, g, b, s2;
-    int n, odd, pad0, pad1;
+    long long n, odd;
 };
 
 // Everything one image-step needs; lives in device memory so that a batch of independent jobs can
@@ -72,6 +73,13 @@ struct EvalJob {
     const int* corner_off;     // NP+1 offsets into `corners`: the triangle corners that sit on each vertex
     const int* corners;        // 3*NT entries, triangle << 2 | corner, grouped by vertex
     EdgeRec* rec;              // NE*9 records
+    // tile path (tiles.cuh)
+    const void* tmap;          // CUtensorMap of the raw image (device memory), box 64 x TH
+    const uint4* coarse;       // prefix at every tile column's left border, column-major [tx][row]
+    int ntx, nty;              // tiles per row / column
+    int2* esnap;               // NE x 10 snapped end points of the nine moves
+    unsigned* ebox;            // NE packed tile ranges (tx0 | tx1 << 8 | ty0 << 16 | ty1 << 24)
+    unsigned* gbox;            // the same, reduced over groups of 32 edges
     const int4* wtri;          // watch topology (the host's triangles / halfedges), may be null
     const int* whe;
     unsigned* wmask;           // one bit per watched triangle: set where a per-frame edit may apply
@@ -188,6 +196,42 @@ __device__ void geterr_serial(const int* __restrict__ ten_base, int nt, float* s
     state[3] = ((double)fabsf(rel) < rel_tol) ? 1.0f : 0.0f;
 }
 
+// ---- the service block (shared by k_edges and k_setup) ---------------------------------------------
+// Pulls the static index arrays k_corners is about to chase through into L2, then runs the previous
+// frame's host-side checks: geterr (one thread) and the topology watch (the others).  See eval.cuh.
+__device__ void service_block(EvalJob& J, int set, unsigned flags, double rel_tol, int frame, int tid, int nthreads, bool single_job)
+{
+    if (!(flags & EV_FINAL) && single_job) {
+        auto prefetch = [&](const void* base, size_t bytes) {
+            const char* p = reinterpret_cast<const char*>(base);
+            for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)nthreads * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+        };
+        prefetch(J.corner_off, sizeof(int) * ((size_t)J.NP + 1));
+        prefetch(J.corners, sizeof(int) * 3 * (size_t)J.NT);
+        prefetch(J.tri_edges, sizeof(int4) * (size_t)J.NT);
+    }
+    if (!(flags & EV_CHECK_PREV)) return;
+    if (tid == 0) *J.trig = 0u;
+    const int words = (J.NT + 31) / 32;
+    const bool hist = (flags & EV_HISTORY) && frame > 0;          // this evaluation checks frame - 1
+    unsigned* const mask = hist ? J.hist_mask + (size_t)(frame - 1) * words : J.wmask;
+    if (J.wtri || hist) for (int w = tid; w < words; w += nthreads) mask[w] = 0u;   // (no watch topology: an empty mask)
+    __syncthreads();
+    if (tid == nthreads - 1) {
+        geterr_serial(J.ten[set ^ 1], J.NT, J.err_state, rel_tol);
+        if (hist) J.hist_err[frame - 1] = J.err_state[0];
+    } else if (J.wtri) {
+        bool hit = false;
+        for (int t = tid; t < J.NT; t += nthreads - 1) {
+            const int code = watch_triangle(J, t);
+            if (code) atomicOr(&mask[t >> 5], 1u << (t & 31));
+            hit |= (flags & EV_HISTORY) ? code == 2 : code != 0;
+        }
+        if (hit) atomicOr(J.trig, (unsigned)kTrigTopology);
+    }
+}
+
 // ---- k_edges ----------------------------------------------------------------------------------
 
 constexpr int kEdgeThreads = 256;
@@ -281,39 +325,7 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
     if ((flags & EV_FINAL) && blockIdx.x != gridDim.x - 1) return;
 
     if (blockIdx.x == gridDim.x - 1) {
-        // service block.  First: pull the static index arrays k_corners is about to chase through
-        // (corner lists, triangle -> edge map, triangles) into L2 while the edges are being walked;
-        // after a cold start each of them would otherwise cost k_corners a DRAM round trip in turn.
-        if (!(flags & EV_FINAL) && gridDim.y == 1) {      // (a batch keeps the memory system busy enough)
-            auto prefetch = [&](const void* base, size_t bytes) {
-                const char* p = reinterpret_cast<const char*>(base);
-                for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)kEdgeThreads * 128)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
-            };
-            prefetch(J.corner_off, sizeof(int) * ((size_t)J.NP + 1));
-            prefetch(J.corners, sizeof(int) * 3 * (size_t)J.NT);
-            prefetch(J.tri_edges, sizeof(int4) * (size_t)J.NT);
-        }
-        // then the previous frame's host-side checks
-        if (!(flags & EV_CHECK_PREV)) return;
-        if (tid == 0) *J.trig = 0u;
-        const int words = (J.NT + 31) / 32;
-        const bool hist = (flags & EV_HISTORY) && frame > 0;          // this evaluation checks frame - 1
-        unsigned* const mask = hist ? J.hist_mask + (size_t)(frame - 1) * words : J.wmask;
-        if (J.wtri || hist) for (int w = tid; w < words; w += kEdgeThreads) mask[w] = 0u;   // (no watch topology: an empty mask)
-        __syncthreads();
-        if (tid == kEdgeThreads - 1) {
-            geterr_serial(J.ten[set ^ 1], J.NT, J.err_state, rel_tol);
-            if (hist) J.hist_err[frame - 1] = J.err_state[0];
-        } else if (J.wtri) {
-            bool hit = false;
-            for (int t = tid; t < J.NT; t += kEdgeThreads - 1) {
-                const int code = watch_triangle(J, t);
-                if (code) atomicOr(&mask[t >> 5], 1u << (t & 31));
-                hit |= (flags & EV_HISTORY) ? code == 2 : code != 0;
-            }
-            if (hit) atomicOr(J.trig, (unsigned)kTrigTopology);
-        }
+        service_block(J, set, flags, rel_tol, frame, tid, kEdgeThreads, gridDim.y == 1);
         return;
     }
 
@@ -358,7 +370,7 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
             EdgeRec rec;
             rec.r = sign * (long long)sr; rec.g = sign * (long long)sg; rec.b = sign * (long long)sb;
             rec.s2 = sign * (long long)s2;
-            rec.n = sign * (int)n; rec.odd = sign * (int)odd; rec.pad0 = 0; rec.pad1 = 0;
+            rec.n = sign * (long long)n; rec.odd = sign * (long long)odd;
             J.rec[item] = rec;
         }
     }
@@ -384,10 +396,9 @@ __device__ __forceinline__ void add_rec(const EdgeRec* __restrict__ recs, int pa
     const int e = packed & 0x7fffffff;
     const int q = (rev && qlocal) ? (qlocal <= 4 ? qlocal + 4 : qlocal - 4) : qlocal;
     const longlong2* p = reinterpret_cast<const longlong2*>(recs + (size_t)e * kEdgeMoves + q);
-    const longlong2 v0 = __ldcg(p), v1 = __ldcg(p + 1);
-    const int2 v2 = __ldcg(reinterpret_cast<const int2*>(p + 2));
-    if (rev) { sr -= v0.x; sg -= v0.y; sb -= v1.x; s2 -= v1.y; n -= v2.x; odd -= v2.y; }
-    else     { sr += v0.x; sg += v0.y; sb += v1.x; s2 += v1.y; n += v2.x; odd += v2.y; }
+    const longlong2 v0 = __ldcg(p), v1 = __ldcg(p + 1), v2 = __ldcg(p + 2);
+    if (rev) { sr -= v0.x; sg -= v0.y; sb -= v1.x; s2 -= v1.y; n -= (int)v2.x; odd -= (int)v2.y; }
+    else     { sr += v0.x; sg += v0.y; sb += v1.x; s2 += v1.y; n += (int)v2.x; odd += (int)v2.y; }
 }
 
 // variant k of triangle t: three edge records -> moments -> cn / ca / ten as the flags ask.

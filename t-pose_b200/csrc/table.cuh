@@ -41,10 +41,10 @@ __device__ __forceinline__ unsigned smem_u32(const void* p)
     return (unsigned)__cvta_generic_to_shared(p);
 }
 
-// One block per image row.  BULK: row bytes are a multiple of 16 and 16-byte aligned.
+// One block per image row.  BULK: rows are 16-byte aligned and ipitch is a multiple of 4 pixels.
 template <bool BULK>
 __global__ void __launch_bounds__(kTableThreads)
-k_build_table(const uchar4* __restrict__ img, int W, int H, uint4* __restrict__ table, int pitch)
+k_build_table(const uchar4* __restrict__ img, int ipitch, int W, int H, uint4* __restrict__ table, int pitch)
 {
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ __align__(8) unsigned long long s_bar;
@@ -53,7 +53,7 @@ k_build_table(const uchar4* __restrict__ img, int W, int H, uint4* __restrict__ 
 
     const int r = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uchar4* row = img + (size_t)r * W;
+    const uchar4* row = img + (size_t)r * ipitch;      // image rows are ipitch pixels apart (a multiple of 4: 16-byte aligned rows)
     uint4* out = table + (size_t)r * pitch;
     const uchar4* src = row;
 
@@ -66,7 +66,7 @@ k_build_table(const uchar4* __restrict__ img, int W, int H, uint4* __restrict__ 
         }
         __syncthreads();
         if (tid == 0) {
-            const unsigned bytes = (unsigned)W * 4u;
+            const unsigned bytes = (unsigned)ipitch * 4u;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
             asm volatile(
                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -110,7 +110,7 @@ k_build_table(const uchar4* __restrict__ img, int W, int H, uint4* __restrict__ 
 // Optional resampler for the reference's 1/1.5 window (Tiny::window(w/1.5, h/1.5),
 // software/triangulate/main.cpp:53): bilinear fetch at the raster pixel centre, float32 with one
 // rounding per operation, truncated to a byte like triangle.fs:31-33 truncates int(255*c).
-__global__ void k_resample(const uchar4* __restrict__ src, int w, int h, uchar4* __restrict__ dst, int rw, int rh)
+__global__ void k_resample(const uchar4* __restrict__ src, int w, int h, uchar4* __restrict__ dst, int rpitch, int rw, int rh)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
@@ -131,7 +131,7 @@ __global__ void k_resample(const uchar4* __restrict__ src, int w, int h, uchar4*
         const float v = __fadd_rn(__fmul_rn(top, __fsub_rn(1.0f, ay)), __fmul_rn(bot, ay));
         return (unsigned char)min(max((int)v, 0), 255);
     };
-    dst[(size_t)j * rw + i] = make_uchar4(mix(p00.x, p10.x, p01.x, p11.x), mix(p00.y, p10.y, p01.y, p11.y),
+    dst[(size_t)j * rpitch + i] = make_uchar4(mix(p00.x, p10.x, p01.x, p11.x), mix(p00.y, p10.y, p01.y, p11.y),
                                           mix(p00.z, p10.z, p01.z, p11.z), 255);
 }
 

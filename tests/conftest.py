@@ -51,3 +51,11 @@ def cuda_pkg(pkg):
 
 def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture(params=["table", "tiles"])
+def kernel_path(request, monkeypatch):
+    """Both edge-integration paths of the library (row-prefix table gathers / TMA-staged tiles) must give
+    the oracle's bits; contexts created inside the test pick the path up from the environment."""
+    monkeypatch.setenv("TPOSE_CUDA_PATH", request.param)
+    return request.param

@@ -21,7 +21,7 @@ import pytest
 
 from conftest import bits
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_path")]
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 

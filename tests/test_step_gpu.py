@@ -4,7 +4,7 @@ import pytest
 
 from conftest import bits
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_path")]
 
 
 def _ctx(pkg, nt=4096, np_=4096):
@@ -100,6 +100,7 @@ def test_adversarial_vertices_on_pixel_centres(cuda_pkg, O):
     img = rng.integers(0, 256, size=(H, W, 4)).astype(np.uint8)
     ctx = _ctx(cuda_pkg, 64, 256)
     ctx.set_image(0, img)
+    gr = None        # pgradbuf lives as long as the context: vertices no triangle references keep stale entries
     for trial in range(40):
         NT = int(rng.integers(1, 12))
         NP = 4 + 3 * NT
@@ -113,8 +114,10 @@ def test_adversarial_vertices_on_pixel_centres(cuda_pkg, O):
             ctx.upload(pts, tri, ratio, cols)
             ctx.step(0, fl, 1)
             got = ctx.retrieve()
-            ref = O.step(img, pts, tri, ratio, fl, colors=cols)
+            ref = O.step(img, pts, tri, ratio, fl, colors=cols, gr=gr)
+            gr = ref["gr"]
             _assert_step_equal(got, ref, ("cn", "ten"))
+            assert np.array_equal(ctx.retrieve_gradient(), gr[:NP])
         ctx.upload_points(pts)   # the step moved the device points; the ID raster is of `pts`
         assert np.array_equal(ctx.raster_ids(0), O.raster_ids(pts, tri, ratio, W, H))
     ctx.close()
@@ -326,6 +329,7 @@ def test_far_offscreen_vertices_take_the_wide_walk(cuda_pkg, O):
     img = rng.integers(0, 256, size=(H, W, 4)).astype(np.uint8)
     ctx = _ctx(cuda_pkg, 64, 256)
     ctx.set_image(0, img)
+    gr = None
     for trial in range(12):
         NT = 6
         NP = 4 + 3 * NT
@@ -340,7 +344,8 @@ def test_far_offscreen_vertices_take_the_wide_walk(cuda_pkg, O):
             ctx.upload(pts, tri, ratio, cols)
             ctx.step(0, fl, 1)
             got = ctx.retrieve()
-            ref = O.step(img, pts, tri, ratio, fl, colors=cols)
+            ref = O.step(img, pts, tri, ratio, fl, colors=cols, gr=gr)
+            gr = ref["gr"]
             _assert_step_equal(got, ref, ("cn", "ten"))
     ctx.close()
 
