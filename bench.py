@@ -121,20 +121,23 @@ def dist_setup(n):
     return rank, world, local, dist
 
 
-def cpu_reference_steps_per_s(O, img, pts, tri, ratio, budget_s, min_steps=1, stride=None):
+def cpu_reference_steps_per_s(O, img, pts, tri, ratio, budget_s, repeats=5):
     """Times the oracle (literal 13*NT-variant, two-pass restatement of the shaders, OpenMP over
-    variants on all host cores).  Returns (steps/s, description)."""
+    variants on all host cores): median of `repeats` runs of n consecutive steps each, n sized so that
+    the whole measurement takes about budget_s (median of 5).  Returns (steps/s, description)."""
     t0 = time.perf_counter()
-    O.step(img, pts, tri, ratio, O.TRIANGULATE)
+    cur = O.step(img, pts, tri, ratio, O.TRIANGULATE)["pts"]
     t_first = time.perf_counter() - t0
-    n = max(min_steps, int(budget_s / max(t_first, 1e-3)))
-    n = min(n, 200)
-    cur = pts
-    t0 = time.perf_counter()
-    for _ in range(n):
-        cur = O.step(img, cur, tri, ratio, O.TRIANGULATE)["pts"]
-    dt = time.perf_counter() - t0
-    return n / dt, f"{n} full steps (all 13*NT variants, both passes) of the same image+mesh, {dt:.1f} s"
+    n = max(1, min(100, int(budget_s / repeats / max(t_first, 1e-3))))
+    rates = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for _ in range(n):
+            cur = O.step(img, cur, tri, ratio, O.TRIANGULATE)["pts"]
+        rates.append(n / (time.perf_counter() - t0))
+    rates.sort()
+    return rates[len(rates) // 2], (f"median of {repeats} runs of {n} full steps (all 13*NT variants, both passes) of the same image+mesh; "
+                                    f"min {rates[0]:.1f} max {rates[-1]:.1f} steps/s")
 
 
 def run_reference(args):
@@ -156,8 +159,8 @@ def run_reference(args):
     O.step(img, pts, tri, ratio, O.TRIANGULATE)
     t_one = time.perf_counter() - t0
     budget = 150.0
-    k = max(1, min(args.steps, int(budget / max(t_one, 1e-3))))
-    wu = max(1, min(args.warmup, 3))
+    wu = max(0, min(args.warmup, int(0.25 * budget / max(t_one, 1e-3))))     # --warmup honoured (bounded only by the time budget)
+    k = max(1, min(args.steps, int(0.75 * budget / max(t_one, 1e-3))))
     cur = pts
     for _ in range(wu):
         cur = O.step(img, cur, tri, ratio, O.TRIANGULATE)["pts"]
@@ -166,19 +169,112 @@ def run_reference(args):
         cur = O.step(img, cur, tri, ratio, O.TRIANGULATE)["pts"]
     dt = time.perf_counter() - t0
     val = k / dt
-    sample = f"{k} full steps of the {w}x{h}/{nt}-triangle workload (requested {args.steps})"
+    sample = f"{k} full steps of the {w}x{h}/{nt}-triangle workload (requested {args.steps}), {wu} warm-up steps (requested {args.warmup})"
     line = {
         "impl": "reference", "metric": "triangulation-opt steps/sec @1080p/3k-tri", "value": val, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": k, "warmup": wu, "ms_per_step": 1000.0 * dt / k, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-        "config": {"workload": f"single {w}x{h} image, {nt} triangles, frozen topology, triangulate flavour",
-                   "note": "the reference's GL path cannot run here (no GL/TinyEngine); this is the CPU port "
-                           "(oracle/step_oracle.c) of its algorithm on the host cores"},
+        "config": shared_config(w, h, tri.shape[0], pts.shape[0], int(os.environ.get("WORLD_SIZE", "1"))),
+        "reference_note": "the reference's GL path cannot run here (no GL/TinyEngine); this is the CPU port "
+                          "(oracle/step_oracle.c) of its algorithm on the host cores",
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def shared_config(w, h, NT, NP, world):
+    """The `config` object both arms print (the driver compares them)."""
+    return {"workload": f"single {w}x{h} image per GPU, {NT} triangles ({NP} points), frozen topology, "
+                        "triangulate flavour (BASELINE.json configs[1])",
+            "raster": "native",
+            "l2": f"GPU arm: L2 flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB write); CPU arm: steps back to back",
+            "parallelism": f"replicas x{world}: one independent image per GPU"}
+
+
+def spread(xs):
+    xs = sorted(xs)
+    return {"min": xs[0], "median": xs[len(xs) // 2], "max": xs[-1]}
+
+
+def synthetic_matches(synth, pts, w, h, ratio, seed):
+    """Matches of one pair as tests/compute_fundamental_mat/main.cpp:137-167 builds them (A's vertices
+    forward, B's backward, both through the effective map (x,y) -> (0.5x/R, -0.5y/R)): the mesh vertices
+    under the known homography of the synthetic view pair + N(0, 0.3 px) noise."""
+    rng = np.random.default_rng(seed)
+    Hm = synth.view_b_homography(w, h)
+    px = np.stack([(pts[:, 0] / ratio + 1.0) * 0.5 * w, (1.0 - pts[:, 1]) * 0.5 * h], 1).astype(np.float64)
+    q = np.concatenate([px, np.ones((len(px), 1))], 1) @ Hm.T
+    q = q[:, :2] / q[:, 2:3] + rng.normal(0.0, 0.3, size=px.shape)
+    back = np.stack([(q[:, 0] / (0.5 * w) - 1.0) * ratio, 1.0 - q[:, 1] / (0.5 * h)], 1)
+    T = lambda P: np.stack([0.5 * P[:, 0] / ratio, -0.5 * P[:, 1] / ratio], 1).astype(np.float32)
+    A = np.concatenate([T(pts), T(back)])          # originpoints -> points of A ; points -> originpoints of B
+    B = np.concatenate([T(back), T(pts)])
+    return A, B
+
+
+def measure_size(pkg, synth, ctx_factory, img_pool, w, h, ntri, K, W, B, barrier, max_over_ranks, peak, with_launches=False):
+    """Cold (L2 flushed, per-step CUDA events), dominant kernel alone, warm (graph replay) and batched numbers
+    for one mesh size; every figure is device time on the context's stream, max over ranks."""
+    ratio = w / h
+    pts, tri, _ = synth.mesh_for(ntri, ratio)
+    NT, NP = tri.shape[0], pts.shape[0]
+    balg = b_alg(w, h, NT, NP)
+    ctx = ctx_factory(NT, NP)
+    ctx.set_image(0, img_pool[0])
+    ctx.upload(pts, tri, ratio)
+    for _ in range(W):
+        ctx.flush_l2(L2_FLUSH_BYTES)
+        ctx.step(0, pkg.TRIANGULATE, 1)
+    barrier(ctx)
+    launches0 = ctx.launch_count()
+    per_step = []
+    for _ in range(K):
+        ctx.flush_l2(L2_FLUSH_BYTES)          # not inside the event bracket of the step
+        ctx.step(0, pkg.TRIANGULATE, 1)       # ev0 . k_edges . k_corners . ev1 on the context's stream
+        per_step.append(ctx.last_elapsed_ms())
+    barrier(ctx)
+    launches = ctx.launch_count() - launches0
+    ms_cold = max_over_ranks(sum(per_step))
+    ctx.set_kernel_timing(True)
+    ms_edges, Kk = 0.0, min(K, 100)
+    for _ in range(Kk):
+        ctx.flush_l2(L2_FLUSH_BYTES)
+        ctx.step(0, pkg.TRIANGULATE, 1)
+        ms_edges += ctx.last_kernel_ms()[0]
+    ctx.set_kernel_timing(False)
+    edges_s = ms_edges / 1000.0 / Kk
+    # same K steps without the flush: the optimiser's steady state (one untimed pass instantiates the graphs)
+    Kw = max(K, 64)
+    ctx.upload(pts, tri, ratio); ctx.step(0, pkg.TRIANGULATE, Kw)
+    ctx.upload(pts, tri, ratio); barrier(ctx)
+    ctx.step(0, pkg.TRIANGULATE, Kw); barrier(ctx)
+    warm_s = max_over_ranks(ctx.last_elapsed_ms()) / 1000.0 / Kw
+    out = {"triangles": NT, "points": NP, "algorithmic_bytes_per_image_step": balg,
+           "cold": {"steps_per_s_per_gpu": K / (ms_cold / 1000.0), "us_per_step": 1000.0 * ms_cold / K,
+                    "us_per_step_spread": {k: 1000.0 * v for k, v in spread(per_step).items()},
+                    "frac_step": balg / (ms_cold / 1000.0 / K) / 1e9 / peak},
+           "kernel": {"name": "k_edges" if ctx.kernel_path() == "table" else "k_tiles", "us": 1e6 * edges_s, "achieved_GBps": balg / edges_s / 1e9,
+                      "frac": balg / edges_s / 1e9 / peak},
+           "warm": {"steps_per_s_per_gpu": 1.0 / warm_s, "us_per_step": 1e6 * warm_s, "frac_step": balg / warm_s / 1e9 / peak}}
+    if B > 1:
+        bctx = [ctx] + [ctx_factory(NT, NP) for _ in range(B - 1)]
+        for i, c in enumerate(bctx):
+            if i:
+                c.set_image(0, img_pool[i % len(img_pool)])
+            c.upload(pts, tri, ratio)
+        Kb = max(16, min(K, 64))
+        pkg.batch_step(bctx, pkg.TRIANGULATE, Kb); barrier(ctx)      # warm-up + graph instantiation
+        pkg.batch_step(bctx, pkg.TRIANGULATE, Kb); barrier(ctx)
+        per = max_over_ranks(ctx.last_elapsed_ms()) / 1000.0 / Kb / B
+        out["batched"] = {"images": B, "steps": Kb, "image_steps_per_s_per_gpu": 1.0 / per, "us_per_image_step": 1e6 * per,
+                          "achieved_GBps": balg / per / 1e9, "frac_step": balg / per / 1e9 / peak}
+        for c in bctx[1:]:
+            c.close()
+        ctx.upload(pts, tri, ratio)
+    out["_ctx"], out["_mesh"], out["_launches"], out["_ms_cold"], out["_edges_s"] = ctx, (pts, tri), launches, ms_cold, edges_s
+    return out
 
 
 def run_ours(args):
@@ -188,16 +284,16 @@ def run_ours(args):
     w, h, nt = args.width, args.height, args.ntri
     ratio = w / h
     K, W = args.steps, max(args.warmup, 3)
-    # every rank owns one independent image (seed 1000 + rank): weak scaling
-    img = synth.make_image(w, h, seed=1000 + rank)
-    pts, tri, _ = synth.mesh_for(nt, ratio)
-    NT, NP = tri.shape[0], pts.shape[0]
-    ctx = pkg.Context(device=local, max_triangles=max(NT, 16), max_points=max(NP, 16))
-    ctx.set_image(0, img)          # image resident in HBM before any timed region
-    ctx.upload(pts, tri, ratio)
+    peak, peak_src = peaks()
+    # every rank owns its own independent images (seeds depend on the rank): weak scaling
+    pool = [synth.make_image(w, h, seed=1000 + rank)] + [synth.make_image(w, h, seed=2000 + 10 * rank + i) for i in range(3)]
+    img = pool[0]
+    def ctx_factory(NT, NP):
+        return pkg.Context(device=local, max_triangles=max(NT, 16), max_points=max(NP, 16))
 
-    def barrier():
-        ctx.sync()
+    def barrier(c=None):
+        if c is not None:
+            c.sync()
         if dist is not None:
             import torch
             dist.barrier()
@@ -211,68 +307,51 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident loop, L2 flushed before every step (rule: flush or exceed L2) ------
-    for _ in range(W):
-        ctx.flush_l2(L2_FLUSH_BYTES)
-        ctx.step(0, pkg.TRIANGULATE, 1)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = ctx.launch_count()
-    barrier()
     t_wall0 = time.perf_counter()
-    ms_cold = 0.0
-    for _ in range(K):
-        ctx.flush_l2(L2_FLUSH_BYTES)          # not inside the event bracket of the step
-        ctx.step(0, pkg.TRIANGULATE, 1)       # ev0 . k_edges . k_corners . ev1 on the context's stream
-        ms_cold += ctx.last_elapsed_ms()
-    barrier()
-    launches = ctx.launch_count() - launches0
-    ms_cold = max_over_ranks(ms_cold)
-    # the dominant kernel alone (an event between the two kernels; not part of the timed K steps)
-    ctx.set_kernel_timing(True)
-    ms_edges, Kk = 0.0, min(K, 100)
-    for _ in range(Kk):
-        ctx.flush_l2(L2_FLUSH_BYTES)
-        ctx.step(0, pkg.TRIANGULATE, 1)
-        ms_edges += ctx.last_kernel_ms()[0]
-    ctx.set_kernel_timing(False)
-    # ---- same K steps without the flush: the optimiser's steady state (table stays in L2).
-    # One untimed pass first, so that the graphs the K steps replay are already instantiated.
-    ctx.upload(pts, tri, ratio)
-    ctx.step(0, pkg.TRIANGULATE, K)
-    ctx.upload(pts, tri, ratio)
-    barrier()
-    ctx.step(0, pkg.TRIANGULATE, K)
-    barrier()
-    ms_warm = max_over_ranks(ctx.last_elapsed_ms())
-    # ---- batch of independent images in lock step (tables exceed L2: the HBM-bound regime) ----
-    B = args.batch
-    batched = None
-    if B > 1:
-        bctx = [ctx] + [pkg.Context(device=local, max_triangles=max(NT, 16), max_points=max(NP, 16)) for _ in range(B - 1)]
-        pool = [img] + [synth.make_image(w, h, seed=2000 + 10 * rank + i) for i in range(3)]   # 4 distinct images, B slots
-        for i, c in enumerate(bctx):
-            if i:
-                c.set_image(0, pool[i % len(pool)])
-            c.upload(pts, tri, ratio)
-        Kb = max(16, min(K, 64))
-        pkg.batch_step(bctx, pkg.TRIANGULATE, Kb)      # warm-up + graph instantiation
-        barrier()
-        pkg.batch_step(bctx, pkg.TRIANGULATE, Kb)
-        barrier()
-        ms_b = max_over_ranks(ctx.last_elapsed_ms())
-        batched = (Kb, ms_b)
-        for c in bctx[1:]:
-            c.close()
-        ctx.upload(pts, tri, ratio)
-    if dist is not None:      # final vertex-buffer gather (the only collective of the job)
+    main = measure_size(pkg, synth, ctx_factory, pool, w, h, nt, K, W, args.batch, barrier, max_over_ranks, peak)
+    ctx = main["_ctx"]
+    pts, tri = main["_mesh"]
+    NT, NP = tri.shape[0], pts.shape[0]
+    # the other two mesh sizes north_star names (secondary lines: fewer steps)
+    sizes = {}
+    for other in ([] if args.no_sizes else [n for n in (1000, 10000) if n != nt]):
+        m = measure_size(pkg, synth, ctx_factory, pool, w, h, other, min(K, 50), W, args.batch, barrier, max_over_ranks, peak)
+        m.pop("_ctx").close()
+        for k in ("_mesh", "_launches", "_ms_cold", "_edges_s"):
+            m.pop(k)
+        sizes[str(m["triangles"])] = m
+    # F + DLT on the device: 64 match lists of 2*NP matches (config 4's tail, batched like config 5 would)
+    mview = None
+    if not args.no_mview:
+        lists = [synthetic_matches(synth, pts, w, h, ratio, seed=500 + 64 * rank + i) for i in range(64)]
+        A, Bm = [a for a, _ in lists], [b for _, b in lists]
+        Kc = np.array([[960 / 673.101, 0, 488.421 / 960], [0, 960 / 673.328, 268.8 / 960], [0, 0, 1]], np.float32)   # mview::Camera(), multiview.hpp:35-52
+        pkg.f8point(A, Bm, device=local)
+        t0 = time.perf_counter()
+        F = pkg.f8point(A, Bm, device=local); ms_f = pkg.mview_last_ms()
+        pkg.triangulate(F, Kc, A, Bm, correct=True, device=local); ms_t = pkg.mview_last_ms()
+        wall = time.perf_counter() - t0
+        mview = {"workload": f"64 match lists x {len(A[0])} matches per GPU: batched F_8Point, then triangulate(F,K,A,B) "
+                             "(optimal correction + pose + HDLT)",
+                 "pairs_per_s_device": world * 64.0 / ((ms_f + ms_t) / 1000.0), "pairs_per_s_host_call": world * 64.0 / wall,
+                 "kernel_ms": {"f8point": ms_f, "triangulate": ms_t},
+                 "note": "device = CUDA-event time of the two kernels; host_call = wall time of the two C-ABI calls with host buffers"}
+    # final vertex-buffer gather (the only collective of the job), timed on its own
+    gather = None
+    if dist is not None:
         import torch
         mine = torch.from_numpy(ctx.retrieve(ten=False, cn=False, ca=False)["pts"]).to(f"cuda:{local}")
         bucket = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        barrier(ctx)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         dist.gather(mine, bucket, dst=0)
+        e1.record()
         torch.cuda.synchronize()
+        gather = {"bytes_per_rank": int(mine.numel() * 4), "ms": max_over_ranks(e0.elapsed_time(e1)), "backend": "nccl"}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the C ABI with host buffers --------------------------------------
@@ -283,9 +362,12 @@ def run_ours(args):
     hpts = pkg.pinned_empty(pts.shape, np.float32); hpts[...] = pts
     hten = pkg.pinned_empty((13 * NT,), np.int32)
     hcn = pkg.pinned_empty((13 * NT,), np.int32)
-    Ke = min(K, 200)
+    Ke = max(K, min(200, 10 * K))
     ctx.upload(pts, tri, ratio)
-    barrier()
+    for _ in range(3):
+        ctx.frame(0, pkg.TRIANGULATE, pts_in=hpts, ten=hten, cn=hcn, pts_out=hpts)
+    hpts[...] = pts
+    barrier(ctx)
     t0 = time.perf_counter()
     ctx.set_image(0, himg)
     for _ in range(Ke):
@@ -297,62 +379,60 @@ def run_ours(args):
     d2h = 13 * NT * (4 + 4) + NP * 8
 
     if rank == 0:
-        peak, peak_src = peaks()
-        balg = b_alg(w, h, NT, NP)
-        cold_s = ms_cold / 1000.0
-        warm_s = ms_warm / 1000.0
-        edges_s = ms_edges / 1000.0 / Kk         # mean duration of one k_edges launch (cold)
+        balg = main["algorithmic_bytes_per_image_step"]
+        cold_s = main["_ms_cold"] / 1000.0
+        edges_s = main["_edges_s"]
         achieved = balg / edges_s / 1e9
-        traffic = None
+        traffic = btraffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("k_edges_dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic, btraffic = tj.get("k_edges_dram_bytes_per_launch"), tj.get("batched_dram_bytes_per_image_step")
             except Exception:
-                traffic = None
+                pass
         line = {
             "metric": "triangulation-opt steps/sec @1080p/3k-tri", "value": world * K / cold_s, "unit": "steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1000.0 * cold_s / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32/i64 (integer moments; float32 vertex update)",
             "data": "synthetic",
-            "config": {"workload": f"single {w}x{h} image per GPU, {NT} triangles ({NP} points), frozen topology, "
-                                   "triangulate flavour (BASELINE.json configs[1])",
-                       "raster": "native", "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB write)",
-                       "parallelism": f"replicas x{world}: one independent image per GPU"},
-            "value_l2_warm": world * K / warm_s,
-            "value_l2_warm_note": "same K steps back to back (CUDA-graph replay), no flush: the optimiser's steady "
+            "config": shared_config(w, h, NT, NP, world),
+            "kernel_path": ctx.kernel_path(),
+            "us_per_step_spread": main["cold"]["us_per_step_spread"],
+            "value_l2_warm": world * main["warm"]["steps_per_s_per_gpu"],
+            "value_l2_warm_note": "same steps back to back (CUDA-graph replay), no flush: the optimiser's steady "
                                   "state (one image's 33 MB table stays L2-resident between its own steps)",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_edges", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": main["kernel"]["name"], "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": balg,
                          "kernel_us": 1e6 * edges_s, "step_us": 1e6 * cold_s / K,
                          "note": "one launch = one image-step of ONE image (latency-bound: 41 k work items cannot "
                                  "fill 148 SMs); see `batched` for the HBM-bound regime",
-                         "frac_step_l2_warm": (balg / (warm_s / K) / 1e9) / peak},
+                         "frac_step_l2_warm": main["warm"]["frac_step"]},
             "e2e": {"value": world * Ke / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": Ke,
                     "what": "set_image from pinned host memory once per job, then per frame tpose_cuda_frame: pointbuf fill (H2D) + "
                             "step + read-back of tenergybuf, tcolnumbuf and pointbuf (13*NT ints each + NP vec2), one sync"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(main["_launches"]),
             "clocks": clocks,
             "wall_s_timed_region": time.perf_counter() - t_wall0,
         }
-        if batched is not None:
-            Kb, ms_b = batched
-            per = ms_b / 1000.0 / Kb / B         # seconds per image-step
-            btraffic = None
-            if os.path.exists(tp):
-                try:
-                    btraffic = json.load(open(tp)).get("batched_dram_bytes_per_image_step")
-                except Exception:
-                    btraffic = None
+        if "batched" in main:
+            bm = main["batched"]
             line["batched"] = {
-                "workload": f"{B} independent {w}x{h} images per GPU in lock step, {NT} triangles each, one launch pair "
-                            f"per step for all of them ({B * 33.2:.0f} MB of tables: larger than L2)",
-                "value": world * 1.0 / per, "unit": "image-steps/s", "steps": Kb, "us_per_image_step": 1e6 * per,
-                "roofline": {"bound": "hbm", "achieved": balg / per / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": balg / per / 1e9 / peak, "traffic": btraffic,
+                "workload": f"{bm['images']} independent {w}x{h} images per GPU in lock step, {NT} triangles each, one launch pair "
+                            f"per step for all of them ({bm['images'] * 33.2:.0f} MB of tables: larger than L2)",
+                "value": world * bm["image_steps_per_s_per_gpu"], "unit": "image-steps/s", "steps": bm["steps"],
+                "us_per_image_step": bm["us_per_image_step"],
+                "roofline": {"bound": "hbm", "achieved": bm["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                             "frac": bm["frac_step"], "traffic": btraffic,
                              "kernel": "k_edges + k_corners (whole step)", "algorithmic_bytes_per_image_step": balg}}
+        if sizes:
+            line["sizes"] = sizes      # 1 000 / 10 000 triangles: cold, dominant kernel, warm, batched -- per GPU, with roofline fractions
+        if mview is not None:
+            line["f_dlt"] = mview
+        if gather is not None:
+            line["gather"] = gather
         if world == 1 and not args.no_cpu_baseline:
             O = entry.load_oracle()
             v, sample = cpu_reference_steps_per_s(O, img, pts, tri, ratio, budget_s=args.cpu_budget)
@@ -376,6 +456,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=64, help="images in the batched (HBM-bound) measurement; 0/1 = skip")
+    ap.add_argument("--no-sizes", action="store_true", help="skip the 1 000 / 10 000-triangle lines")
+    ap.add_argument("--no-mview", action="store_true", help="skip the F + DLT line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -261,6 +261,17 @@ int tpose_cuda_f8point(int device, const float *A_xy, const float *B_xy, const i
  * solves re-weighted by the Sampson denominators of the current estimate.  Same outputs as above. */
 int tpose_cuda_fsampson(int device, const float *A_xy, const float *B_xy, const float *weights,
                         const int *offsets, int nbatch, int iterations, float *F9_out);
+/* Match selection and weighting by two-way warp inconsistency -- the step the reference keeps as commented-out
+ * code in tests/compute_fundamental_mat/model.h:1-82.  For every vertex i of view A, then of view B:
+ * d_i = |warp_origin[i] - points[i]| (the other direction's .warp record against this one); the vertex becomes a
+ * match with weight 1/d_i unless d_i > max_dist (the reference: 0.0000002), an end point lies on the domain
+ * boundary or outside the central half of the domain.  A's matches run originpoints -> points, B's
+ * points -> originpoints, both mapped (x, y) -> ((0.5f/RATIO) x, (-0.5f/RATIO) y).  X_xy / Y_xy / weights: room
+ * for npa + npb entries; *n_out: matches kept (index order, A's first); dist (may be NULL): all npa + npb d_i.
+ * The outputs feed tpose_cuda_fsampson(.., weights, ..). */
+int tpose_cuda_select_matches(int device, const float *originA_xy, const float *pointsA_xy, const float *warp_originA_xy, int npa,
+                              const float *pointsB_xy, const float *originB_xy, const float *warp_originB_xy, int npb,
+                              float ratio, double max_dist, float *X_xy, float *Y_xy, float *weights, float *dist, int *n_out);
 /* mview::triangulate(F, K, A, B) (multiview.hpp:529-627): per match the Hartley-Sturm optimal
  * correction (:415-527; skipped if optimal_correction == 0), then HDLT (:370-380) against
  * PA = K[I|0], PB = K[R2|-t] from E = K^T F K (check = 3).  F9 / K9: one 3x3 per list.

@@ -255,3 +255,40 @@ def f_sampson(pa, pb, w=None, iters=100):
         F = _rank2(Vt[8].astype(f32).astype(np.float64).reshape(3, 3)).astype(f32)
     Fd = HB.astype(np.float64).T @ F.astype(np.float64) @ HA.astype(np.float64)
     return Fd / Fd[2, 2]
+
+
+def select_matches(originA, pointsA, warp_originA, pointsB, originB, warp_originB, ratio, max_dist=0.0000002):
+    """tests/compute_fundamental_mat/model.h:1-82 (commented out in the reference), loop for loop:
+    returns (matchX, matchY, weights, dist2D) -- dist2D for all vertices of A then of B."""
+    R = f32(ratio)
+    cx, cy = f32(0.5) / R, f32(-0.5) / R                   # T, a row-major literal in a column-major glm::mat3 (model.h:7-11)
+
+    def T(p):
+        return np.array([(cx * p[0] + f32(0.0) * p[1]) + f32(0.0), (f32(0.0) * p[0] + cy * p[1]) + f32(0.0)], f32)
+
+    def boundary(p):                                       # triangulation.hpp:132-140
+        return p[0] <= -R or p[1] <= f32(-1) or p[0] >= R or p[1] >= f32(1)
+
+    def central(p):
+        return not (float(p[0]) < -float(R) / 2.0 or float(p[0]) > float(R) / 2.0 or float(p[1]) < -0.5 or float(p[1]) > 0.5)
+
+    X, Y, W, D = [], [], [], []
+    for (first, second, worig, a_side) in ((originA, pointsA, warp_originA, True), (pointsB, originB, warp_originB, False)):
+        first = np.asarray(first, f32).reshape(-1, 2); second = np.asarray(second, f32).reshape(-1, 2)
+        worig = np.asarray(worig, f32).reshape(-1, 2)
+        pts = second if a_side else first                  # tr.points of this view
+        for i in range(len(first)):
+            dv = (worig[i] - pts[i]).astype(f32)
+            d = f32(np.sqrt(f32(f32(dv[0] * dv[0]) + f32(dv[1] * dv[1]))))
+            D.append(d)
+            pX, pY = first[i], second[i]
+            if float(d) > max_dist:
+                continue
+            if boundary(pX) or boundary(pY):
+                continue
+            if not central(pX) or not central(pY):
+                continue
+            X.append(T(pX)); Y.append(T(pY))
+            with np.errstate(divide="ignore"):
+                W.append(f32(1.0) / d)
+    return (np.array(X, f32).reshape(-1, 2), np.array(Y, f32).reshape(-1, 2), np.array(W, f32), np.array(D, f32))

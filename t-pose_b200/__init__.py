@@ -43,7 +43,7 @@ EXPORTS = [
     "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
     "tpose_cuda_raster_ids", "tpose_cuda_render", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_last_setup_ms", "tpose_cuda_kernel_path", "tpose_cuda_set_kernel_timing", "tpose_cuda_set_step_scale", "tpose_cuda_sync",
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
-    "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_carry", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
+    "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_select_matches", "tpose_cuda_carry", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
     "tpose_cuda_mview_last_ms",
     "tpose_cuda_watch", "tpose_cuda_watch_mask", "tpose_cuda_set_history", "tpose_cuda_history_frame", "tpose_cuda_history_restore_gradient", "tpose_cuda_read", "tpose_cuda_write", "tpose_cuda_batch_step", "tpose_cuda_batch_run",
 ]
@@ -335,6 +335,21 @@ def fsampson(A_lists, B_lists, weights=None, iterations=100, device=0):
     _mview_ck(lib().tpose_cuda_fsampson(device, _ptr(A), _ptr(B), _ptr(W), _ptr(offs), len(A_lists),
                                         C.c_int(iterations), _ptr(F)), "fsampson")
     return F.reshape(-1, 3, 3)
+
+
+def select_matches(originA, pointsA, warp_originA, pointsB, originB, warp_originB, ratio, max_dist=0.0000002, device=0):
+    """Two-way-inconsistency match selection (compute_fundamental_mat/model.h:1-82): (X, Y, weights, dist)."""
+    f = lambda a: np.ascontiguousarray(np.asarray(a, np.float32).reshape(-1, 2))
+    oA, pA, wA, pB, oB, wB = map(f, (originA, pointsA, warp_originA, pointsB, originB, warp_originB))
+    npa, npb = len(pA), len(pB)
+    n = max(npa + npb, 1)
+    X = np.zeros((n, 2), np.float32); Y = np.zeros((n, 2), np.float32); W = np.zeros(n, np.float32); D = np.zeros(n, np.float32)
+    kept = C.c_int()
+    _mview_ck(lib().tpose_cuda_select_matches(device, _ptr(oA), _ptr(pA), _ptr(wA), npa, _ptr(pB), _ptr(oB), _ptr(wB), npb,
+                                              C.c_float(ratio), C.c_double(max_dist), _ptr(X), _ptr(Y), _ptr(W), _ptr(D), C.byref(kept)),
+              "select_matches")
+    k = kept.value
+    return X[:k], Y[:k], W[:k], D[:npa + npb]
 
 
 def triangulate(F, K, A_lists, B_lists, correct=True, device=0):

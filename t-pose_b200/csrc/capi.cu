@@ -1304,15 +1304,31 @@ extern "C" int tpose_cuda_flush_l2(tpose_cuda_ctx* ctx, size_t bytes)
 // ---- multiview (source/multiview.hpp) -----------------------------------------------------------
 
 namespace {
-std::string g_mview_error;
-float g_mview_ms = 0.0f;
+// The multiview entry points take no context: their state -- last error, last kernel time and a
+// grow-only device workspace with its own stream and events per device -- is per host thread, so
+// they are thread-compatible like the context API, and a call costs no cudaMalloc / cudaFree.
+thread_local std::string g_mview_error;
+thread_local float g_mview_ms = 0.0f;
 
-struct DevBuf {                       // RAII device allocation for one call
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-    template <typename T> T* as() { return (T*)p; }
+struct MviewWs {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    unsigned char* buf = nullptr; size_t cap = 0, used = 0;
+    ~MviewWs()
+    {
+        if (device < 0) return;
+        // (thread exit: release quietly; the primary context may already be gone at process exit)
+        if (cudaSetDevice(device) == cudaSuccess) {
+            if (buf) cudaFree(buf);
+            if (e0) cudaEventDestroy(e0);
+            if (e1) cudaEventDestroy(e1);
+            if (stream) cudaStreamDestroy(stream);
+        }
+        (void)cudaGetLastError();
+    }
 };
+thread_local std::vector<MviewWs*> g_mview_ws;
 
 int mview_fail(int code, const std::string& msg) { g_mview_error = msg; return code; }
 
@@ -1322,16 +1338,44 @@ int mview_fail(int code, const std::string& msg) { g_mview_error = msg; return c
         if (e_ != cudaSuccess) return mview_fail(TPOSE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
-int mview_device(int device)
+// the calling thread's workspace on `device`, holding at least `bytes`
+int mview_workspace(int device, size_t bytes, MviewWs** out)
 {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
         (void)cudaGetLastError();
         return mview_fail(TPOSE_ERR_NODEVICE, "no usable CUDA device (this library has no CPU fallback)");
     }
-    if (cudaSetDevice(device) != cudaSuccess) return mview_fail(TPOSE_ERR_CUDA, "cudaSetDevice failed");
+    MCK(cudaSetDevice(device));
+    MviewWs* ws = nullptr;
+    for (MviewWs* w : g_mview_ws) if (w->device == device) ws = w;
+    if (!ws) {
+        ws = new MviewWs();
+        ws->device = device;
+        MCK(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+        MCK(cudaEventCreate(&ws->e0)); MCK(cudaEventCreate(&ws->e1));
+        g_mview_ws.push_back(ws);
+    }
+    if (ws->cap < bytes) {
+        MCK(cudaStreamSynchronize(ws->stream));
+        if (ws->buf) cudaFree(ws->buf);
+        ws->buf = nullptr; ws->cap = 0;
+        const size_t want = bytes + bytes / 2 + 4096;
+        MCK(cudaMalloc((void**)&ws->buf, want));
+        ws->cap = want;
+    }
+    ws->used = 0;
+    *out = ws;
     return TPOSE_OK;
 }
+
+template <typename T> T* carve(MviewWs* ws, size_t count)
+{
+    T* p = reinterpret_cast<T*>(ws->buf + ws->used);
+    ws->used += (count * sizeof(T) + 255) & ~(size_t)255;
+    return p;
+}
+size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
 
 bool offsets_ok(const int* offsets, int nbatch)
 {
@@ -1349,29 +1393,26 @@ static int fmatrix_common(int device, const float* A_xy, const float* B_xy, cons
 {
     if (!A_xy || !B_xy || !F9_out || !offsets_ok(offsets, nbatch) || iters < 0)
         return mview_fail(TPOSE_ERR_ARG, std::string(who) + ": bad arguments");
-    int rc = mview_device(device);
-    if (rc) return rc;
     const size_t n = (size_t)offsets[nbatch];
-    DevBuf dA, dB, dO, dF, dW;
-    MCK(dA.alloc(n * sizeof(float2))); MCK(dB.alloc(n * sizeof(float2)));
-    MCK(dO.alloc((nbatch + 1) * sizeof(int))); MCK(dF.alloc((size_t)nbatch * 9 * sizeof(float)));
-    MCK(cudaMemcpy(dA.p, A_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dB.p, B_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dO.p, offsets, (nbatch + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    if (weights) {
-        MCK(dW.alloc(n * sizeof(float)));
-        MCK(cudaMemcpy(dW.p, weights, n * sizeof(float), cudaMemcpyHostToDevice));
-    }
-    cudaEvent_t e0, e1;
-    MCK(cudaEventCreate(&e0)); MCK(cudaEventCreate(&e1));
-    MCK(cudaEventRecord(e0, 0));
-    k_f8point<<<nbatch, kF8Threads>>>(dA.as<float2>(), dB.as<float2>(), dO.as<int>(), weights ? dW.as<float>() : nullptr, iters,
-                                      dF.as<float>());
-    MCK(cudaEventRecord(e1, 0));
+    MviewWs* ws = nullptr;
+    int rc = mview_workspace(device, 2 * padded(n * sizeof(float2)) + padded((nbatch + 1) * sizeof(int)) +
+                                         padded((size_t)nbatch * 9 * sizeof(float)) + padded(n * sizeof(float)) + 1024, &ws);
+    if (rc) return rc;
+    float2* dA = carve<float2>(ws, n); float2* dB = carve<float2>(ws, n);
+    int* dO = carve<int>(ws, nbatch + 1); float* dF = carve<float>(ws, (size_t)nbatch * 9);
+    float* dW = weights ? carve<float>(ws, n) : nullptr;
+    cudaStream_t st = ws->stream;
+    MCK(cudaMemcpyAsync(dA, A_xy, n * sizeof(float2), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dB, B_xy, n * sizeof(float2), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dO, offsets, (nbatch + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (weights) MCK(cudaMemcpyAsync(dW, weights, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    MCK(cudaEventRecord(ws->e0, st));
+    k_f8point<<<nbatch, kF8Threads, 0, st>>>(dA, dB, dO, dW, iters, dF);
+    MCK(cudaEventRecord(ws->e1, st));
     MCK(cudaGetLastError());
-    MCK(cudaMemcpy(F9_out, dF.p, (size_t)nbatch * 9 * sizeof(float), cudaMemcpyDeviceToHost));
-    cudaEventElapsedTime(&g_mview_ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    MCK(cudaMemcpyAsync(F9_out, dF, (size_t)nbatch * 9 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&g_mview_ms, ws->e0, ws->e1);
     return TPOSE_OK;
 }
 
@@ -1391,39 +1432,81 @@ extern "C" int tpose_cuda_triangulate(int device, const float* F9, const float* 
                                       float* A_corr, float* B_corr)
 {
     if (!F9 || !K9 || !A_xy || !B_xy || !X4_out || !offsets_ok(offsets, nbatch)) return mview_fail(TPOSE_ERR_ARG, "triangulate: bad arguments");
-    int rc = mview_device(device);
-    if (rc) return rc;
     const size_t n = (size_t)offsets[nbatch];
     int longest = 0;
     for (int i = 0; i < nbatch; i++) longest = std::max(longest, offsets[i + 1] - offsets[i]);
-    DevBuf dA, dB, dO, dF, dK, dX, dAc, dBc;
-    MCK(dA.alloc(n * sizeof(float2))); MCK(dB.alloc(n * sizeof(float2)));
-    MCK(dO.alloc((nbatch + 1) * sizeof(int)));
-    MCK(dF.alloc((size_t)nbatch * 9 * sizeof(float))); MCK(dK.alloc((size_t)nbatch * 9 * sizeof(float)));
-    MCK(dX.alloc(n * sizeof(float4)));
-    if (A_corr) MCK(dAc.alloc(n * sizeof(float2)));
-    if (B_corr) MCK(dBc.alloc(n * sizeof(float2)));
-    MCK(cudaMemcpy(dA.p, A_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dB.p, B_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dO.p, offsets, (nbatch + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dF.p, F9, (size_t)nbatch * 9 * sizeof(float), cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dK.p, K9, (size_t)nbatch * 9 * sizeof(float), cudaMemcpyHostToDevice));
-    cudaEvent_t e0, e1;
-    MCK(cudaEventCreate(&e0)); MCK(cudaEventCreate(&e1));
-    MCK(cudaEventRecord(e0, 0));
+    MviewWs* ws = nullptr;
+    int rc = mview_workspace(device, 4 * padded(n * sizeof(float2)) + padded((nbatch + 1) * sizeof(int)) +
+                                         2 * padded((size_t)nbatch * 9 * sizeof(float)) + padded(n * sizeof(float4)) + 1024, &ws);
+    if (rc) return rc;
+    float2* dA = carve<float2>(ws, n); float2* dB = carve<float2>(ws, n);
+    int* dO = carve<int>(ws, nbatch + 1);
+    float* dF = carve<float>(ws, (size_t)nbatch * 9); float* dK = carve<float>(ws, (size_t)nbatch * 9);
+    float4* dX = carve<float4>(ws, n);
+    float2* dAc = A_corr ? carve<float2>(ws, n) : nullptr;
+    float2* dBc = B_corr ? carve<float2>(ws, n) : nullptr;
+    cudaStream_t st = ws->stream;
+    MCK(cudaMemcpyAsync(dA, A_xy, n * sizeof(float2), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dB, B_xy, n * sizeof(float2), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dO, offsets, (nbatch + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dF, F9, (size_t)nbatch * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dK, K9, (size_t)nbatch * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+    MCK(cudaEventRecord(ws->e0, st));
     if (longest > 0) {
         const dim3 grid((longest + 127) / 128, nbatch);
-        k_triangulate<<<grid, 128>>>(dF.as<float>(), dK.as<float>(), dA.as<float2>(), dB.as<float2>(), dO.as<int>(),
-                                     optimal_correction, dX.as<float4>(), A_corr ? dAc.as<float2>() : nullptr,
-                                     B_corr ? dBc.as<float2>() : nullptr);
+        k_triangulate<<<grid, 128, 0, st>>>(dF, dK, dA, dB, dO, optimal_correction, dX, dAc, dBc);
     }
-    MCK(cudaEventRecord(e1, 0));
+    MCK(cudaEventRecord(ws->e1, st));
     MCK(cudaGetLastError());
-    MCK(cudaMemcpy(X4_out, dX.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
-    if (A_corr) MCK(cudaMemcpy(A_corr, dAc.p, n * sizeof(float2), cudaMemcpyDeviceToHost));
-    if (B_corr) MCK(cudaMemcpy(B_corr, dBc.p, n * sizeof(float2), cudaMemcpyDeviceToHost));
-    cudaEventElapsedTime(&g_mview_ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    MCK(cudaMemcpyAsync(X4_out, dX, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    if (A_corr) MCK(cudaMemcpyAsync(A_corr, dAc, n * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    if (B_corr) MCK(cudaMemcpyAsync(B_corr, dBc, n * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&g_mview_ms, ws->e0, ws->e1);
+    return TPOSE_OK;
+}
+
+extern "C" int tpose_cuda_select_matches(int device, const float* originA_xy, const float* pointsA_xy, const float* warp_originA_xy, int npa,
+                                         const float* pointsB_xy, const float* originB_xy, const float* warp_originB_xy, int npb,
+                                         float ratio, double max_dist, float* X_xy, float* Y_xy, float* weights, float* dist, int* n_out)
+{
+    if (npa < 0 || npb < 0 || !X_xy || !Y_xy || !weights || !n_out || (npa > 0 && (!originA_xy || !pointsA_xy || !warp_originA_xy)) ||
+        (npb > 0 && (!pointsB_xy || !originB_xy || !warp_originB_xy)) || !(ratio > 0.0f))
+        return mview_fail(TPOSE_ERR_ARG, "select_matches: bad arguments");
+    *n_out = 0;
+    const size_t n = (size_t)npa + (size_t)npb;
+    if (n == 0) return TPOSE_OK;
+    MviewWs* ws = nullptr;
+    int rc = mview_workspace(device, 8 * padded(n * sizeof(float2)) + 2 * padded(n * sizeof(float)) + 2048, &ws);
+    if (rc) return rc;
+    float2* dOA = carve<float2>(ws, npa); float2* dPA = carve<float2>(ws, npa); float2* dWA = carve<float2>(ws, npa);
+    float2* dPB = carve<float2>(ws, npb); float2* dOB = carve<float2>(ws, npb); float2* dWB = carve<float2>(ws, npb);
+    float2* dX = carve<float2>(ws, n); float2* dY = carve<float2>(ws, n); float* dW = carve<float>(ws, n); float* dD = carve<float>(ws, n);
+    int* dN = carve<int>(ws, 1);
+    cudaStream_t st = ws->stream;
+    if (npa) {
+        MCK(cudaMemcpyAsync(dOA, originA_xy, sizeof(float2) * npa, cudaMemcpyHostToDevice, st));
+        MCK(cudaMemcpyAsync(dPA, pointsA_xy, sizeof(float2) * npa, cudaMemcpyHostToDevice, st));
+        MCK(cudaMemcpyAsync(dWA, warp_originA_xy, sizeof(float2) * npa, cudaMemcpyHostToDevice, st));
+    }
+    if (npb) {
+        MCK(cudaMemcpyAsync(dPB, pointsB_xy, sizeof(float2) * npb, cudaMemcpyHostToDevice, st));
+        MCK(cudaMemcpyAsync(dOB, originB_xy, sizeof(float2) * npb, cudaMemcpyHostToDevice, st));
+        MCK(cudaMemcpyAsync(dWB, warp_originB_xy, sizeof(float2) * npb, cudaMemcpyHostToDevice, st));
+    }
+    k_select_matches<<<1, kSelectThreads, 0, st>>>(dOA, dPA, dWA, npa, dPB, dOB, dWB, npb, ratio, max_dist, dX, dY, dW, dist ? dD : nullptr, dN);
+    MCK(cudaGetLastError());
+    int kept = 0;
+    MCK(cudaMemcpyAsync(&kept, dN, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    if (kept > 0) {
+        MCK(cudaMemcpyAsync(X_xy, dX, sizeof(float2) * kept, cudaMemcpyDeviceToHost, st));
+        MCK(cudaMemcpyAsync(Y_xy, dY, sizeof(float2) * kept, cudaMemcpyDeviceToHost, st));
+        MCK(cudaMemcpyAsync(weights, dW, sizeof(float) * kept, cudaMemcpyDeviceToHost, st));
+    }
+    if (dist) MCK(cudaMemcpyAsync(dist, dD, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    *n_out = kept;
     return TPOSE_OK;
 }
 
@@ -1435,17 +1518,19 @@ extern "C" int tpose_cuda_carry(int device, const int32_t* tri_xyzw, int nt, con
     for (int t = 0; t < nt; t++)
         for (int k = 0; k < 3; k++)
             if (tri_xyzw[4 * t + k] < 0 || tri_xyzw[4 * t + k] >= nv) return mview_fail(TPOSE_ERR_ARG, "carry: triangle references a vertex outside [0,nv)");
-    int rc = mview_device(device);
+    MviewWs* ws = nullptr;
+    int rc = mview_workspace(device, padded(sizeof(int4) * nt) + 2 * padded(sizeof(float2) * nv) + padded(sizeof(float2) * npts) + 1024, &ws);
     if (rc) return rc;
-    DevBuf dT, dF, dTo, dP;
-    MCK(dT.alloc(sizeof(int4) * nt)); MCK(dF.alloc(sizeof(float2) * nv)); MCK(dTo.alloc(sizeof(float2) * nv)); MCK(dP.alloc(sizeof(float2) * npts));
-    MCK(cudaMemcpy(dT.p, tri_xyzw, sizeof(int4) * nt, cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dF.p, from_xy, sizeof(float2) * nv, cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dTo.p, to_xy, sizeof(float2) * nv, cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dP.p, pts_xy, sizeof(float2) * npts, cudaMemcpyHostToDevice));
-    k_carry<<<(npts + kCarryThreads - 1) / kCarryThreads, kCarryThreads>>>(dT.as<int4>(), nt, dF.as<float2>(), dTo.as<float2>(), dP.as<float2>(), npts, ratio);
+    int4* dT = carve<int4>(ws, nt); float2* dF = carve<float2>(ws, nv); float2* dTo = carve<float2>(ws, nv); float2* dP = carve<float2>(ws, npts);
+    cudaStream_t st = ws->stream;
+    MCK(cudaMemcpyAsync(dT, tri_xyzw, sizeof(int4) * nt, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dF, from_xy, sizeof(float2) * nv, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dTo, to_xy, sizeof(float2) * nv, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dP, pts_xy, sizeof(float2) * npts, cudaMemcpyHostToDevice, st));
+    k_carry<<<(npts + kCarryThreads - 1) / kCarryThreads, kCarryThreads, 0, st>>>(dT, nt, dF, dTo, dP, npts, ratio);
     MCK(cudaGetLastError());
-    MCK(cudaMemcpy(pts_xy, dP.p, sizeof(float2) * npts, cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpyAsync(pts_xy, dP, sizeof(float2) * npts, cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
     return TPOSE_OK;
 }
 
@@ -1453,17 +1538,19 @@ extern "C" int tpose_cuda_hdlt(int device, const float* PA12, const float* PB12,
                                int n, float* X4_out)
 {
     if (!PA12 || !PB12 || !A_xy || !B_xy || !X4_out || n < 1) return mview_fail(TPOSE_ERR_ARG, "hdlt: bad arguments");
-    int rc = mview_device(device);
+    MviewWs* ws = nullptr;
+    int rc = mview_workspace(device, 2 * padded(n * sizeof(float2)) + 2 * padded(12 * sizeof(float)) + padded(n * sizeof(float4)) + 1024, &ws);
     if (rc) return rc;
-    DevBuf dA, dB, dPA, dPB, dX;
-    MCK(dA.alloc(n * sizeof(float2))); MCK(dB.alloc(n * sizeof(float2)));
-    MCK(dPA.alloc(12 * sizeof(float))); MCK(dPB.alloc(12 * sizeof(float))); MCK(dX.alloc(n * sizeof(float4)));
-    MCK(cudaMemcpy(dA.p, A_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dB.p, B_xy, n * sizeof(float2), cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dPA.p, PA12, 12 * sizeof(float), cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dPB.p, PB12, 12 * sizeof(float), cudaMemcpyHostToDevice));
-    k_hdlt<<<(n + 127) / 128, 128>>>(dPA.as<float>(), dPB.as<float>(), dA.as<float2>(), dB.as<float2>(), n, dX.as<float4>());
+    float2* dA = carve<float2>(ws, n); float2* dB = carve<float2>(ws, n);
+    float* dPA = carve<float>(ws, 12); float* dPB = carve<float>(ws, 12); float4* dX = carve<float4>(ws, n);
+    cudaStream_t st = ws->stream;
+    MCK(cudaMemcpyAsync(dA, A_xy, n * sizeof(float2), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dB, B_xy, n * sizeof(float2), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dPA, PA12, 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dPB, PB12, 12 * sizeof(float), cudaMemcpyHostToDevice, st));
+    k_hdlt<<<(n + 127) / 128, 128, 0, st>>>(dPA, dPB, dA, dB, n, dX);
     MCK(cudaGetLastError());
-    MCK(cudaMemcpy(X4_out, dX.p, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpyAsync(X4_out, dX, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
     return TPOSE_OK;
 }

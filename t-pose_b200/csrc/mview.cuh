@@ -18,45 +18,94 @@ namespace tpose_dev {
 
 constexpr int kF8Threads = 256;
 
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// block-wide sum of `v` (all threads get the result); s_red holds kF8Threads/32 doubles
-__device__ double block_sum(double v, double* s_red)
-{
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int w = 0; w < kF8Threads / 32; w++) t += s_red[w];
-    return t;
-}
-
 struct Norm { float cx, cy, scale; };
 
-// multiview.hpp:62-87 -- centroid, mean distance, scale sqrt(2)/dist.  The reference sums in float32
-// in index order; here the sums are float64 tree reductions (the difference is far below the 1e-4
-// parity bound, and any (c, scale) is undone exactly by the returned H).
-__device__ Norm normalise_stats(const float2* __restrict__ p, int n, double* s_red)
+constexpr int kNormChunk = 2048;          // values staged per pass of the in-order float32 sums
+
+// multiview.hpp:62-87 -- centroid, mean distance, scale sqrt(2)/dist, LITERALLY: the reference adds
+// float32 values in index order (`c += p`, `dist += length(p)`), and float addition is not
+// associative, so the sums are taken by one thread in that order; the addends (p, then
+// length(p - c) with glm's sqrt(dot)) are produced by the whole block, a chunk at a time.
+// s_val: 2 * kNormChunk floats.  All threads get the result.
+__device__ Norm normalise_stats(const float2* __restrict__ p, int n, float* s_val, float* s_out)
 {
-    double sx = 0.0, sy = 0.0;
-    for (int i = threadIdx.x; i < n; i += kF8Threads) { sx += p[i].x; sy += p[i].y; }
-    const double tx = block_sum(sx, s_red), ty = block_sum(sy, s_red);
-    Norm r;
-    r.cx = (float)(tx / n); r.cy = (float)(ty / n);
-    double sd = 0.0;
-    for (int i = threadIdx.x; i < n; i += kF8Threads) {
-        const float dx = __fsub_rn(p[i].x, r.cx), dy = __fsub_rn(p[i].y, r.cy);
-        sd += (double)__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    float cx = 0.0f, cy = 0.0f;
+    for (int c0 = 0; c0 < n; c0 += kNormChunk) {
+        const int m = min(kNormChunk, n - c0);
+        for (int i = threadIdx.x; i < m; i += kF8Threads) { s_val[2 * i] = p[c0 + i].x; s_val[2 * i + 1] = p[c0 + i].y; }
+        __syncthreads();
+        if (threadIdx.x == 0) for (int i = 0; i < m; i++) { cx = __fadd_rn(cx, s_val[2 * i]); cy = __fadd_rn(cy, s_val[2 * i + 1]); }
+        __syncthreads();
     }
-    const float dist = (float)(block_sum(sd, s_red) / n);
-    r.scale = (float)(sqrt(2.0) / (double)dist);
+    if (threadIdx.x == 0) { s_out[0] = __fdiv_rn(cx, (float)n); s_out[1] = __fdiv_rn(cy, (float)n); }
+    __syncthreads();
+    Norm r;
+    r.cx = s_out[0]; r.cy = s_out[1];
+    float dist = 0.0f;
+    for (int c0 = 0; c0 < n; c0 += kNormChunk) {
+        const int m = min(kNormChunk, n - c0);
+        for (int i = threadIdx.x; i < m; i += kF8Threads) {
+            const float dx = __fsub_rn(p[c0 + i].x, r.cx), dy = __fsub_rn(p[c0 + i].y, r.cy);
+            s_val[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));       // glm::length
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) for (int i = 0; i < m; i++) dist = __fadd_rn(dist, s_val[i]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s_out[2] = (float)(sqrt(2.0) / (double)__fdiv_rn(dist, (float)n));   // `float scale = sqrt(2) / dist`
+    __syncthreads();
+    r.scale = s_out[2];
+    __syncthreads();
     return r;
+}
+
+// tpose::sm::jacobi_eigen<9> (cyclic Jacobi, smallmath.h) with the rotations in the same order and
+// every element updated by the same expression, so the result is the serial one bit for bit -- but
+// the nine rows / columns of a rotation are updated by nine lanes at once (and V by nine more).
+// Called by one full warp; A (destroyed) and V are 81 doubles in shared memory.
+__device__ void jacobi_eigen9_warp(double* A, double* V)
+{
+    constexpr int N = 9;
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < N * N; i += 32) V[i] = (i / N == i % N) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 30; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < N; i++) {                       // (every lane: same values, same order as the serial code)
+            diag += A[i * N + i] * A[i * N + i];
+            for (int j = i + 1; j < N; j++) off += A[i * N + j] * A[i * N + j];
+        }
+        if (off <= 1e-36 * diag || off == 0.0) break;
+        for (int p = 0; p < N - 1; p++)
+            for (int q = p + 1; q < N; q++) {
+                const double apq = A[p * N + q];
+                if (apq == 0.0) continue;                   // (uniform: every lane read the same element)
+                const double theta = (A[q * N + q] - A[p * N + p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                __syncwarp();
+                if (lane < N) {                             // columns p, q
+                    const int k = lane;
+                    const double akp = A[k * N + p], akq = A[k * N + q];
+                    A[k * N + p] = c * akp - s * akq;
+                    A[k * N + q] = s * akp + c * akq;
+                } else if (lane < 2 * N) {
+                    const int k = lane - N;
+                    const double vkp = V[k * N + p], vkq = V[k * N + q];
+                    V[k * N + p] = c * vkp - s * vkq;
+                    V[k * N + q] = s * vkp + c * vkq;
+                }
+                __syncwarp();
+                if (lane < N) {                             // rows p, q
+                    const int k = lane;
+                    const double apk = A[p * N + k], aqk = A[q * N + k];
+                    A[p * N + k] = c * apk - s * aqk;
+                    A[q * N + k] = s * apk + c * aqk;
+                }
+                __syncwarp();
+            }
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ float2 normalise_point(float2 p, const Norm& nm)
@@ -146,8 +195,9 @@ __device__ void solve_normalised(const float2* __restrict__ pa, const float2* __
     if (lane == 0) atomicAdd(&s_G[80], g88);
     __syncthreads();
 
+    if (threadIdx.x < 32) jacobi_eigen9_warp(s_G, s_V);
+    __syncthreads();
     if (threadIdx.x == 0) {
-        tpose::sm::jacobi_eigen<9>(s_G, s_V);
         const int m = tpose::sm::argmin_diag<9>(s_G);
         for (int i = 0; i < 9; i++) F[i] = (double)(float)s_V[i * 9 + m];      // VectorXf f -> Matrix3f F
         tpose::sm::rank2_project(F);
@@ -177,7 +227,8 @@ __global__ void __launch_bounds__(kF8Threads)
 k_f8point(const float2* __restrict__ A, const float2* __restrict__ B, const int* __restrict__ offsets,
           const float* __restrict__ wuser, int iters, float* __restrict__ F9)
 {
-    __shared__ double s_red[kF8Threads / 32];
+    __shared__ float s_val[2 * kNormChunk];
+    __shared__ float s_out[4];
     __shared__ double s_G[81];                 // A^T A
     __shared__ double s_V[81];
     __shared__ float s_F[9];
@@ -190,8 +241,8 @@ k_f8point(const float2* __restrict__ A, const float2* __restrict__ B, const int*
     }
     const float2* pa = A + o0;
     const float2* pb = B + o0;
-    const Norm na = normalise_stats(pa, n, s_red);
-    const Norm nb = normalise_stats(pb, n, s_red);
+    const Norm na = normalise_stats(pa, n, s_val, s_out);
+    const Norm nb = normalise_stats(pb, n, s_val, s_out);
     double F[9], R[9];
     solve_normalised(pa, pb, n, na, nb, nullptr, nullptr, s_G, s_V, F);
     if (threadIdx.x == 0) {
@@ -252,6 +303,80 @@ k_triangulate(const float* __restrict__ F9, const float* __restrict__ K9, const 
     double X[4];
     tpose::sm::hdlt(s_KPA, s_KPB, a, b, X);
     X4[o0 + i] = make_float4((float)(X[0] / X[3]), (float)(X[1] / X[3]), (float)(X[2] / X[3]), 1.0f);
+}
+
+// ---- match selection by two-way warp inconsistency (tests/compute_fundamental_mat/model.h:1-82) -----
+// The reference keeps this step as commented-out code: from the two warped stacks of a view pair
+// (tr = the level as warp left it, trW = the same level of the other direction's .warp stack) it
+// takes, for every vertex i of A and then of B,
+//     d_i = length(trW.originpoints[i] - tr.points[i])                            model.h:22,52
+// and keeps the vertex as a match (weight 1/d_i) unless d_i > max_dist (:27,:60; 2e-7 as coded),
+// either end lies on the domain boundary (:30-32) or outside the central half of the domain
+// (:34-41).  A's matches run originpoints -> points, B's points -> originpoints (:24-25,:54-55),
+// both through T, which -- a row-major literal in a column-major glm::mat3 -- maps
+// (x, y) -> ((0.5f/RATIO) x, (-0.5f/RATIO) y) (model.h:7-11).
+// One block; the kept matches are compacted in index order (A's first), so the output is the
+// vector the reference's push_backs would build.  out_n[0] = number of matches.
+constexpr int kSelectThreads = 512;
+
+__device__ __forceinline__ bool domain_boundary(float2 p, float ratio)           // triangulation.hpp:132-140
+{
+    return p.x <= -ratio || p.y <= -1.0f || p.x >= ratio || p.y >= 1.0f;
+}
+
+__global__ void __launch_bounds__(kSelectThreads)
+k_select_matches(const float2* __restrict__ originA, const float2* __restrict__ pointsA, const float2* __restrict__ worigA, int npa,
+                 const float2* __restrict__ pointsB, const float2* __restrict__ originB, const float2* __restrict__ worigB, int npb,
+                 float ratio, double max_dist, float2* __restrict__ X, float2* __restrict__ Y, float* __restrict__ Wt,
+                 float* __restrict__ dist_out, int* __restrict__ out_n)
+{
+    __shared__ int s_warp[kSelectThreads / 32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    const float cx = __fdiv_rn(0.5f, ratio), cy = __fdiv_rn(-0.5f, ratio);
+    const int total = npa + npb;
+    for (int c0 = 0; c0 < total; c0 += kSelectThreads) {
+        const int i = c0 + tid;
+        bool keep = false;
+        float2 pX = make_float2(0.0f, 0.0f), pY = pX;
+        float d = 0.0f;
+        if (i < total) {
+            const bool isA = i < npa;
+            const int k = isA ? i : i - npa;
+            const float2 wo = isA ? worigA[k] : worigB[k];
+            const float2 pt = isA ? pointsA[k] : pointsB[k];
+            const float2 og = isA ? originA[k] : originB[k];
+            const float dx = __fsub_rn(wo.x, pt.x), dy = __fsub_rn(wo.y, pt.y);
+            d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+            if (dist_out) dist_out[i] = d;
+            pX = isA ? og : pt;                    // A: originpoints -> points; B: points -> originpoints
+            pY = isA ? pt : og;
+            keep = !((double)d > max_dist) && !domain_boundary(pX, ratio) && !domain_boundary(pY, ratio);
+            const double hx = (double)ratio / 2.0, hy = 1.0 / 2.0;
+            if ((double)pX.x < -hx || (double)pX.x > hx || (double)pX.y < -hy || (double)pX.y > hy) keep = false;
+            if ((double)pY.x < -hx || (double)pY.x > hx || (double)pY.y < -hy || (double)pY.y > hy) keep = false;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int before = s_base;
+        for (int w2 = 0; w2 < wid; w2++) before += s_warp[w2];
+        if (keep) {
+            const int at = before + __popc(bal & ((1u << lane) - 1u));
+            // T * vec3(p, 1): (c x + 0 y) + 0 in float32, like glm's mat3 * vec3
+            X[at] = make_float2(__fadd_rn(__fadd_rn(__fmul_rn(cx, pX.x), __fmul_rn(0.0f, pX.y)), 0.0f),
+                                __fadd_rn(__fadd_rn(__fmul_rn(0.0f, pX.x), __fmul_rn(cy, pX.y)), 0.0f));
+            Y[at] = make_float2(__fadd_rn(__fadd_rn(__fmul_rn(cx, pY.x), __fmul_rn(0.0f, pY.y)), 0.0f),
+                                __fadd_rn(__fadd_rn(__fmul_rn(0.0f, pY.x), __fmul_rn(cy, pY.y)), 0.0f));
+            Wt[at] = __fdiv_rn(1.0f, d);
+        }
+        __syncthreads();
+        if (tid == 0) { int t = s_base; for (int w2 = 0; w2 < kSelectThreads / 32; w2++) t += s_warp[w2]; s_base = t; }
+        __syncthreads();
+    }
+    if (tid == 0) out_n[0] = s_base;
 }
 
 // HDLT alone with caller-supplied 3x4 projections (multiview.hpp:370-380); X is NOT divided by w,

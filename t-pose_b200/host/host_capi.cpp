@@ -259,6 +259,24 @@ void tph_fsampson(const float* A, int na, const float* B, int nb, const float* w
                : tpose::mview::F_Sampson(vec2s(A, na), vec2s(B, nb));
     std::memcpy(F9, F.m, sizeof F.m);
 }
+// tpose::mview::select_matches over plain arrays (a level of A / B and of the other direction's stacks)
+void tph_select_matches(const float* originA, const float* pointsA, const float* worigA, int npa, const float* pointsB,
+                        const float* originB, const float* worigB, int npb, float ratio, double max_dist, float* X, float* Y,
+                        float* W, int* n_out)
+{
+    struct Lvl { std::vector<glm::vec2> points, originpoints; };
+    Lvl a, wa, b, wb;
+    a.originpoints = vec2s(originA, npa); a.points = vec2s(pointsA, npa); wa.originpoints = vec2s(worigA, npa);
+    b.originpoints = vec2s(originB, npb); b.points = vec2s(pointsB, npb); wb.originpoints = vec2s(worigB, npb);
+    std::vector<glm::vec2> mx, my; std::vector<float> w;
+    tpose::mview::select_matches(a, wa, b, wb, ratio, mx, my, w, max_dist);
+    *n_out = (int)mx.size();
+    if (!mx.empty()) {
+        std::memcpy(X, mx.data(), sizeof(glm::vec2) * mx.size());
+        std::memcpy(Y, my.data(), sizeof(glm::vec2) * my.size());
+        std::memcpy(W, w.data(), sizeof(float) * w.size());
+    }
+}
 void tph_triangulate_points(const float* F9, const float* K9, const float* A, const float* B, int n, float* X4)
 {
     tpose::mview::Matrix3f F, K;

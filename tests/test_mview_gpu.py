@@ -55,7 +55,8 @@ def test_f8point_golden_and_batched(cuda_pkg):
 def test_fsampson_golden_batched_weighted(cuda_pkg):
     """mview::F_Sampson (multiview.hpp:187-299).  The iteration re-derives float32 weights from a
     float32 F a hundred times; between two consecutive iterations of the oracle itself F/F(2,2)
-    moves by ~2e-5, so the bound here is 5e-4 (written down in DESIGN.md section 7)."""
+    moves by ~2e-5; with the normalisation summed like the reference (float32, index order) the device
+    iterates on the very same normalised points as the oracle and the north_star bound of 1e-4 holds."""
     g = np.load(GOLD)
     rng = np.random.default_rng(1)
     As, Bs = [g["A"]], [g["B"]]
@@ -63,10 +64,10 @@ def test_fsampson_golden_batched_weighted(cuda_pkg):
         a, b = _synthetic_pair(rng, n, 2e-3)
         As.append(a); Bs.append(b)
     F = cuda_pkg.fsampson(As, Bs)
-    assert _close(F[0], g["F_sampson"], 5e-4), np.abs(F[0] - g["F_sampson"]).max() / np.abs(g["F_sampson"]).max()
+    assert _close(F[0], g["F_sampson"], 1e-4), np.abs(F[0] - g["F_sampson"]).max() / np.abs(g["F_sampson"]).max()
     for i in range(1, len(As)):
         ref = M.f_sampson(As[i], Bs[i])
-        assert _close(F[i], ref, 5e-4), (i, np.abs(F[i] - ref).max() / np.abs(ref).max())
+        assert _close(F[i], ref, 1e-4), (i, np.abs(F[i] - ref).max() / np.abs(ref).max())
     # zero iterations is F_8Point
     assert np.array_equal(cuda_pkg.fsampson(As, Bs, iterations=0), cuda_pkg.f8point(As, Bs))
     # unit weights change nothing; real weights follow the three-argument overload
@@ -76,7 +77,7 @@ def test_fsampson_golden_batched_weighted(cuda_pkg):
     Fw = cuda_pkg.fsampson(As, Bs, weights=w)
     for i in (0, 2):
         ref = M.f_sampson(As[i], Bs[i], w=w[i])
-        assert _close(Fw[i], ref, 5e-4), (i, np.abs(Fw[i] - ref).max() / np.abs(ref).max())
+        assert _close(Fw[i], ref, 1e-4), (i, np.abs(Fw[i] - ref).max() / np.abs(ref).max())
     # empty list -> identity, like F_8Point
     Fe = cuda_pkg.fsampson([np.zeros((0, 2), np.float32)], [np.zeros((0, 2), np.float32)])
     assert np.array_equal(Fe[0], np.eye(3, dtype=np.float32))
@@ -147,3 +148,47 @@ def test_hdlt_and_host_header_path(cuda_pkg):
     Xs = np.zeros(4, np.float32)
     L.f("hdlt")(H._p(KPA.reshape(12)), H._p(KPB.reshape(12)), H._p(g["A"][0]), H._p(g["B"][0]), H._p(Xs))
     assert _close(Xs.astype(np.float64) / Xs[3], g["X_nc"][0])
+
+
+def test_select_matches_two_way_inconsistency(cuda_pkg, synth):
+    """tests/compute_fundamental_mat/model.h:1-82 (dead code in the reference, restated loop for loop by
+    oracle/mview_oracle.select_matches): same matches, same order, same float32 weights -- bit for bit --
+    and the weights drive F_Sampson's three-argument overload."""
+    rng = np.random.default_rng(5)
+    ratio = 1920 / 1080
+    pts, tri, _ = synth.mesh_for(3000, ratio)
+    NP = len(pts)
+    f = np.float32
+    originA = pts.copy()
+    shift = (rng.normal(0, 0.01, pts.shape)).astype(f)
+    pointsA = (pts + shift).astype(f)
+    pointsA[:4] = pts[:4]
+    # the other direction's stack disagrees by a little, by nothing, or by a lot
+    noise = rng.choice([0.0, 1e-7, 3e-4, 5e-2], size=(NP, 1)).astype(f) * rng.normal(0, 1, pts.shape).astype(f)
+    worigA = (pointsA + noise).astype(f)
+    pointsB = (pts - shift).astype(f); originB = pts.copy()
+    worigB = (pointsB + noise[::-1]).astype(f)
+    for max_dist in (0.0000002, 1e-3, 10.0):
+        X, Y, W, D = cuda_pkg.select_matches(originA, pointsA, worigA, pointsB, originB, worigB, ratio, max_dist)
+        rX, rY, rW, rD = M.select_matches(originA, pointsA, worigA, pointsB, originB, worigB, ratio, max_dist)
+        assert X.shape == rX.shape and len(X) > 0
+        assert np.array_equal(X.view(np.uint32), rX.view(np.uint32)) and np.array_equal(Y.view(np.uint32), rY.view(np.uint32))
+        assert np.array_equal(W.view(np.uint32), rW.view(np.uint32)) and np.array_equal(D.view(np.uint32), rD.view(np.uint32))
+    assert np.isinf(W).any()                      # d = 0 -> weight 1/0, as coded
+    # finite weights into the weighted Sampson iteration
+    X, Y, W, _ = cuda_pkg.select_matches(originA, pointsA, worigA, pointsB, originB, worigB, ratio, 1e-3)
+    ok = np.isfinite(W)
+    X, Y, W = X[ok], Y[ok], np.minimum(W[ok], f(1e6))
+    Fw = cuda_pkg.fsampson([X], [Y], weights=[W])[0]
+    ref = M.f_sampson(X, Y, w=W)
+    assert _close(Fw, ref, 1e-4), np.abs(Fw - ref).max() / np.abs(ref).max()
+    # C++ header entry point (tpose::mview::select_matches) builds the same vectors
+    L = H.ours()
+    if hasattr(L.lib, "tph_select_matches"):
+        n = C.c_int()
+        oX = np.zeros((2 * NP, 2), f); oY = np.zeros((2 * NP, 2), f); oW = np.zeros(2 * NP, f)
+        L.f("select_matches")(H._p(originA), H._p(pointsA), H._p(worigA), NP, H._p(pointsB), H._p(originB), H._p(worigB), NP,
+                              C.c_float(ratio), C.c_double(1e-3), H._p(oX), H._p(oY), H._p(oW), C.byref(n))
+        rX, rY, rW, _ = M.select_matches(originA, pointsA, worigA, pointsB, originB, worigB, ratio, 1e-3)
+        assert n.value == len(rX) and np.array_equal(oX[:n.value].view(np.uint32), rX.view(np.uint32))
+        assert np.array_equal(oW[:n.value].view(np.uint32), rW.view(np.uint32))
