@@ -277,6 +277,84 @@ def measure_size(pkg, synth, ctx_factory, img_pool, w, h, ntri, K, W, B, barrier
     return out
 
 
+def run_config5(args, pkg, synth, rank, world, local, dist, barrier, max_over_ranks, ctx):
+    """64 view pairs (1920x1080, 4-level stacks 150 -> 3 000 triangles) through the warp level loop, F_8Point and
+    triangulate(F,K,A,B), 64/world pairs per rank in one process per GPU (include/tpose/pairs: all pairs of a rank share
+    launches), and ONE NCCL gather of every pair's vertex buffers + F + 3-D vertices to rank 0 -- inside the timed
+    region.  Strong scaling: the 64 pairs are fixed.  Rank 0 then recomputes a pair another rank owned: same bytes."""
+    import shutil
+    import tempfile
+    P = importlib.import_module("tpose_b200.pairs")
+    w, h = args.width, args.height
+    ratio = float(np.float32(w) / np.float32(h))
+    total, cap = args.pairs, args.pair_level_cap
+    sizes = (150, 500, 1500, 3000)
+    share = [g for g in range(total) if g % world == rank]          # global pair indices of this rank
+    work = tempfile.mkdtemp(prefix=f"tpose_pairs_r{rank}_")
+    pool = []                                                         # two distinct pairs, the same on every rank
+    for k in range(2):
+        a, b = synth.make_pair(w, h, seed=3000 + k)
+        ta, tb = os.path.join(work, f"pool{k}a.tri"), os.path.join(work, f"pool{k}b.tri")
+        P.grid_stack(pkg, synth, ta, a, ratio, sizes, device=local); P.grid_stack(pkg, synth, tb, b, ratio, sizes, device=local)
+        pool.append((a, b, ta, tb))
+
+    def build(indices):
+        ps = P.PairSet(local)
+        for g in indices:
+            a, b, ta, tb = pool[g % 2]
+            pa, pb = os.path.join(work, f"p{g}a.tri"), os.path.join(work, f"p{g}b.tri")
+            shutil.copy(ta, pa); shutil.copy(tb, pb)
+            ps.add(a, b, pa, pb, max_triangles=max(sizes), max_points=max(sizes))
+        return ps
+
+    ps = build(share)
+    barrier(ctx)
+    t0 = time.perf_counter()
+    frames, levels = ps.run(tol=1e-6, level_cap=cap)
+    packed = [ps.packed(i) for i in range(len(share))]
+    t_compute = time.perf_counter() - t0
+    length = len(packed[0]) if packed else 0
+    gather_ms, gathered = 0.0, None
+    if dist is not None:
+        import torch
+        mine = torch.from_numpy(np.stack(packed)).to(f"cuda:{local}")          # every pair has the same mesh sizes here
+        bucket = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.gather(mine, bucket, dst=0)
+        e1.record()
+        torch.cuda.synchronize()
+        gather_ms = e0.elapsed_time(e1)
+        if rank == 0:
+            gathered = [t.cpu().numpy() for t in bucket]
+    t_total = max_over_ranks(time.perf_counter() - t0)
+    gather_ms = max_over_ranks(gather_ms)
+    t_compute = max_over_ranks(t_compute)
+    ps.close()
+    out = None
+    if rank == 0:
+        # sharding must not change results: recompute the last pair (owned by the last rank) here
+        g = total - 1
+        chk = build([g])
+        chk.run(tol=1e-6, level_cap=cap)
+        again = chk.packed(0)
+        chk.close()
+        owner, slot = g % world, [x for x in range(total) if x % world == (g % world)].index(g)
+        theirs = gathered[owner][slot] if gathered is not None else packed[slot]
+        identical = bool(np.array_equal(again.view(np.uint32), np.asarray(theirs, np.float32).view(np.uint32)))
+        assert identical, "config 5: a pair recomputed on rank 0 differs from the gathered one"
+        out = {"workload": f"{total} independent {w}x{h} view pairs (2 distinct synthetic pairs cycled), grid stacks {list(sizes)} triangles, warp level "
+                           f"loop (geterr < 1e-6 or {cap} frames per level -- the time box is an extension, see include/tpose/pairs) + F_8Point + "
+                           "triangulate(F,K,A,B), all pairs of a rank in shared launches, one process per GPU",
+               "pairs_per_s": total / t_total, "seconds": t_total, "compute_seconds_max_rank": t_compute,
+               "frames_per_pair": int(frames[0]), "levels_per_pair": int(levels[0]), "pairs_per_rank": len(share),
+               "gather": {"collective": "torch.distributed.gather over NCCL, inside the timed region" if dist is not None else "single rank: nothing to gather",
+                          "bytes_per_pair": int(4 * length), "bytes_total": int(4 * length * total), "ms": gather_ms},
+               "recomputed_pair_identical": identical, "scaling": "strong"}
+    shutil.rmtree(work, ignore_errors=True)
+    return out
+
+
 def run_ours(args):
     rank, world, local, dist = dist_setup(args.gpus)
     pkg = entry.load_package()
@@ -339,6 +417,10 @@ def run_ours(args):
                  "pairs_per_s_device": world * 64.0 / ((ms_f + ms_t) / 1000.0), "pairs_per_s_host_call": world * 64.0 / wall,
                  "kernel_ms": {"f8point": ms_f, "triangulate": ms_t},
                  "note": "device = CUDA-event time of the two kernels; host_call = wall time of the two C-ABI calls with host buffers"}
+    # ---- BASELINE configs[4]: 64 independent 1080p pairs, 3 000-triangle warp + F + DLT, sharded over the ranks ----
+    config5 = None
+    if not args.no_pairs:
+        config5 = run_config5(args, pkg, synth, rank, world, local, dist, barrier, max_over_ranks, ctx)
     # final vertex-buffer gather (the only collective of the job), timed on its own
     gather = None
     if dist is not None:
@@ -433,6 +515,8 @@ def run_ours(args):
             line["f_dlt"] = mview
         if gather is not None:
             line["gather"] = gather
+        if config5 is not None:
+            line["config5"] = config5
         if world == 1 and not args.no_cpu_baseline:
             O = entry.load_oracle()
             v, sample = cpu_reference_steps_per_s(O, img, pts, tri, ratio, budget_s=args.cpu_budget)
@@ -458,6 +542,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="images in the batched (HBM-bound) measurement; 0/1 = skip")
     ap.add_argument("--no-sizes", action="store_true", help="skip the 1 000 / 10 000-triangle lines")
     ap.add_argument("--no-mview", action="store_true", help="skip the F + DLT line")
+    ap.add_argument("--no-pairs", action="store_true", help="skip the 64-pair warp + F + DLT pipeline (BASELINE configs[4])")
+    ap.add_argument("--pairs", type=int, default=64)
+    ap.add_argument("--pair-level-cap", type=int, default=250, help="frames per warp level at most (time box of the pair pipeline)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

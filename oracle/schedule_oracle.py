@@ -170,14 +170,17 @@ def triangulate_loop(R, Tri, img, ratio, exportlist, trifile, max_frames, tol=1e
     return out
 
 
-def warp_loop(R, Tri, img_a, img_b, triA, triB, max_frames, tol=1e-6):
-    """software/warp/main.cpp:112-284.  Writes triA+'.warp' / triB+'.warp'."""
+def warp_loop(R, Tri, img_a, img_b, triA, triB, max_frames, tol=1e-6, level_cap=-1):
+    """software/warp/main.cpp:112-284.  Writes triA+'.warp' / triB+'.warp'.
+    level_cap > 0 (not in the reference; mirrors tpose::pairs::warp_batch): a level also ends after that many
+    frames.  The returned dict carries the frames each level took."""
     import ctypes as C
     R.f("set_toterr")(C.c_float(1.0))                           # a fresh process: toterr starts at 1 (triangulation.hpp:648)
     trA, trB = Tri(R), Tri(R)
     trA.read(triA); trB.read(triB)                              # main.cpp:115-116
     warpA = True
     frames, levels, finished = 0, 0, False
+    level_frames, per_level = 0, []
     state = {}
 
     def upload(tr):                                             # upload(tr): colours replicated 13x
@@ -200,9 +203,10 @@ def warp_loop(R, Tri, img_a, img_b, triA, triB, max_frames, tol=1e-6):
         state["gr"] = gr
         state["pts"] = O.shift(state["pts"], gr[:len(state["pts"])], ratio, O.WARP)
         frames += 1
+        level_frames += 1
         R.f("set_terr")(ten.ctypes.data_as(C.c_void_p), len(ten))
         tr.set_points(state["pts"])
-        if float(tr.geterr()) < tol:                            # main.cpp:231
+        if float(tr.geterr()) < tol or (level_cap > 0 and level_frames >= level_cap):   # main.cpp:231
             if warpA:                                           # main.cpp:235-243
                 sB = trB.get()
                 trB.set_points(trA.warp(sB["opts"], reverse=True))
@@ -213,10 +217,11 @@ def warp_loop(R, Tri, img_a, img_b, triA, triB, max_frames, tol=1e-6):
             tr = trA if warpA else trB
             trA.write(triA + ".warp"); trB.write(triB + ".warp")   # main.cpp:269-270
             levels += 1
+            per_level.append(level_frames); level_frames = 0
             if not trA.read(triA, True) or not trB.read(triB, True):
                 finished = True
                 break
             upload(tr)
-    out = dict(frames=frames, levels=levels, finished=finished, A=trA.get(), B=trB.get())
+    out = dict(frames=frames, levels=levels, finished=finished, per_level=per_level, A=trA.get(), B=trB.get())
     trA.close(); trB.close()
     return out

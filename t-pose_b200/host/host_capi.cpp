@@ -8,6 +8,7 @@
 #include <tpose/schedule>
 #include <tpose/detail/edgeview.h>
 #include <tpose/multiview>
+#include <tpose/pairs>
 
 #include <sstream>
 
@@ -228,6 +229,59 @@ void tph_warp(const char* triA, const char* triB, long max_frames, double tol, l
     rep7[0] = r.frames; rep7[1] = r.host_frames; rep7[2] = r.runs; rep7[3] = r.splits; rep7[4] = r.exports; rep7[5] = r.levels; rep7[6] = r.finished;
 }
 
+
+// ---- tpose/pairs: BASELINE configs 4 / 5 in one process per GPU ----------------------------------------
+// A set of independent view pairs on one device.  tph_init(device) first (device-side warp / reversewarp).
+struct PairSet {
+    int device = 0;
+    std::vector<std::unique_ptr<tpose::pairs::job>> jobs;
+    ~PairSet() { for (auto& j : jobs) if (j->ctx) tpose_cuda_destroy(j->ctx); }
+};
+void* tph_pairs_new(int device) { auto* s = new PairSet(); s->device = device; return s; }
+void tph_pairs_free(void* h) { delete (PairSet*)h; }
+// adds a pair: both views' pixels (w x h RGBA8, rasterised at rw x rh) and the two .tri stacks; returns its index or < 0
+int tph_pairs_add(void* h, const unsigned char* rgbaA, const unsigned char* rgbaB, int w, int hgt, int rw, int rh,
+                  const char* triA, const char* triB, int max_triangles, int max_points)
+{
+    auto* s = (PairSet*)h;
+    auto j = std::make_unique<tpose::pairs::job>();
+    if (tpose_cuda_create(s->device, max_triangles, max_points, nullptr, &j->ctx) != TPOSE_OK) return -1;
+    if (tpose_cuda_set_image(j->ctx, TPOSE_IMAGE_A, rgbaA, w, hgt, rw, rh) != TPOSE_OK) return -2;
+    if (tpose_cuda_set_image(j->ctx, TPOSE_IMAGE_B, rgbaB, w, hgt, rw, rh) != TPOSE_OK) return -3;
+    j->triA = triA; j->triB = triB;
+    Quiet q;
+    tpose::pairs::open(*j);
+    s->jobs.push_back(std::move(j));
+    return (int)s->jobs.size() - 1;
+}
+// warp level loop of all pairs, then F + 3-D points for all of them; frames / levels: one entry per pair
+void tph_pairs_run(void* h, double tol, long level_cap, int with_mview, long* frames, long* levels)
+{
+    auto* s = (PairSet*)h;
+    std::vector<tpose::pairs::job*> js;
+    for (auto& j : s->jobs) js.push_back(j.get());
+    Quiet q;
+    tpose::pairs::warp_batch(js, tol, level_cap, false);
+    if (with_mview) tpose::pairs::fundamental_and_points(js, s->device);
+    for (size_t i = 0; i < js.size(); i++) { if (frames) frames[i] = js[i]->frames; if (levels) levels[i] = js[i]->levels; }
+}
+// sizes of pair i's results: [NP of A, NP of B, matches]
+void tph_pairs_sizes(void* h, int i, int* out3)
+{
+    auto& j = *((PairSet*)h)->jobs[(size_t)i];
+    out3[0] = (int)j.trA.points.size(); out3[1] = (int)j.trB.points.size(); out3[2] = (int)j.X.size();
+}
+// pair i's results: finest level's vertex buffers (points | originpoints of A, then of B), F, the 3-D vertices
+void tph_pairs_result(void* h, int i, float* ptsA, float* optsA, float* ptsB, float* optsB, float* F9, float* X4)
+{
+    auto& j = *((PairSet*)h)->jobs[(size_t)i];
+    if (ptsA) std::memcpy(ptsA, j.trA.points.data(), sizeof(glm::vec2) * j.trA.points.size());
+    if (optsA) std::memcpy(optsA, j.trA.originpoints.data(), sizeof(glm::vec2) * j.trA.originpoints.size());
+    if (ptsB) std::memcpy(ptsB, j.trB.points.data(), sizeof(glm::vec2) * j.trB.points.size());
+    if (optsB) std::memcpy(optsB, j.trB.originpoints.data(), sizeof(glm::vec2) * j.trB.originpoints.size());
+    if (F9) std::memcpy(F9, j.F.m, sizeof j.F.m);
+    if (X4 && !j.X.empty()) std::memcpy(X4, j.X.data(), sizeof(glm::vec4) * j.X.size());
+}
 
 // ---- tpose/multiview ---------------------------------------------------------------------------------
 

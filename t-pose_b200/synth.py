@@ -77,7 +77,7 @@ def make_pair(w, h, seed=1000):
     return a, warp_image(a, view_b_homography(w, h))
 
 
-GRIDS = {150: (15, 5), 1000: (25, 20), 3000: (50, 30), 10000: (100, 50)}
+GRIDS = {150: (15, 5), 500: (25, 10), 1000: (25, 20), 1500: (30, 25), 3000: (50, 30), 10000: (100, 50)}
 
 
 def grid_mesh(nx, ny, ratio, seed=7, jitter=0.2):
