@@ -191,6 +191,16 @@ int tpose_cuda_history_restore_gradient(tpose_cuda_ctx *ctx, int frame);
  * per-frame loops without changing their result.  nwords >= (NT+31)/32. */
 int tpose_cuda_watch_mask(tpose_cuda_ctx *ctx, uint32_t *mask_words, int nwords);
 
+/* A few instances evaluated on their own, at the context's current points: entry i = (v0, v1, v2, k) -- three
+ * vertex indices and a variant number k (0 = the triangle as it is, 1 + 4j + s = corner j moved by +-dp like
+ * triangle.vs:66-78; dp from the uploaded NT) -- yields what the full triangulate-flavour evaluation would put
+ * in row k of a triangle with those vertices: cn (fragment count), ca (colour sums), ten (energy against the
+ * instance's own mean colour, triangle.fs:27-43).  Nothing of the context's SSBOs is touched.  This is the
+ * device half of the flip set of a converged frame (software/triangulate/main.cpp:287-306 re-rasterises all
+ * 13*NT instances twice to read a few base energies).  Needs the table path.  Outputs may be NULL. */
+int tpose_cuda_eval_list(tpose_cuda_ctx *ctx, int slot, const int32_t *entries_v0v1v2k, int n,
+                         int32_t *ten_out, int32_t *cn_out, int32_t *ca_out_rgba);
+
 /* ---- batches of independent jobs --------------------------------------------
  * n contexts on the same device advance in lock step, one launch per frame for all of them
  * (blockIdx.y = job).  Jobs are independent problems (own image, mesh, buffers); results are

@@ -45,7 +45,7 @@ EXPORTS = [
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
     "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_select_matches", "tpose_cuda_carry", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
     "tpose_cuda_mview_last_ms",
-    "tpose_cuda_watch", "tpose_cuda_watch_mask", "tpose_cuda_set_history", "tpose_cuda_history_frame", "tpose_cuda_history_restore_gradient", "tpose_cuda_read", "tpose_cuda_write", "tpose_cuda_batch_step", "tpose_cuda_batch_run",
+    "tpose_cuda_watch", "tpose_cuda_watch_mask", "tpose_cuda_set_history", "tpose_cuda_eval_list", "tpose_cuda_history_frame", "tpose_cuda_history_restore_gradient", "tpose_cuda_read", "tpose_cuda_write", "tpose_cuda_batch_step", "tpose_cuda_batch_run",
 ]
 
 
@@ -174,6 +174,14 @@ class Context:
         ten = np.empty(self.NT, np.int32); tot = C.c_float()
         self._ck(lib().tpose_cuda_history_frame(self._h, C.c_int(frame), _ptr(pts), _ptr(m), nw, _ptr(ten), C.byref(tot)))
         return dict(pts=pts, mask=np.unpackbits(m.view(np.uint8), bitorder="little")[:self.NT].astype(bool), ten=ten, toterr=tot.value)
+
+    def eval_list(self, slot, entries):
+        """entries (n, 4) int32 = (v0, v1, v2, k): (ten, cn, ca) of those instances at the current points."""
+        en = np.ascontiguousarray(entries, np.int32).reshape(-1, 4)
+        n = en.shape[0]
+        ten = np.zeros(n, np.int32); cn = np.zeros(n, np.int32); ca = np.zeros((n, 4), np.int32)
+        self._ck(lib().tpose_cuda_eval_list(self._h, slot, _ptr(en), n, _ptr(ten), _ptr(cn), _ptr(ca)))
+        return ten, cn, ca
 
     def history_restore_gradient(self, frame):
         self._ck(lib().tpose_cuda_history_restore_gradient(self._h, C.c_int(frame)))

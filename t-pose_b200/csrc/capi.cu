@@ -90,6 +90,7 @@ struct tpose_cuda_ctx {
     EvalJob* batch_jobs = nullptr; int batch_cap = 0;   // job array when this context leads a batch
     int* ids = nullptr; size_t ids_cap = 0;
     unsigned char* flush = nullptr; size_t flush_cap = 0;
+    unsigned char* list_buf = nullptr; size_t list_cap = 0;     // tpose_cuda_eval_list scratch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;   // ev_mid: between k_edges / k_tiles and k_corners of a single step
     cudaEvent_t ev_mid0 = nullptr;    // tile path: between k_setup and k_tiles
     cudaEvent_t ev_batch = nullptr;   // end of the last batch this context led (the other jobs' streams wait on it)
@@ -262,7 +263,7 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
     cudaFree(ctx->staging); cudaFree(ctx->tri);
     cudaFree(ctx->edges); cudaFree(ctx->tri_edges); cudaFree(ctx->corner_off); cudaFree(ctx->corners); cudaFree(ctx->rec);
     cudaFree(ctx->gr); cudaFree(ctx->wbuf); cudaFree(ctx->ticket);
-    cudaFree(ctx->report); cudaFree(ctx->ids); cudaFree(ctx->flush);
+    cudaFree(ctx->report); cudaFree(ctx->ids); cudaFree(ctx->flush); cudaFree(ctx->list_buf);
     cudaFree(ctx->job_dev); cudaFree(ctx->batch_jobs);
     if (ctx->h_report) cudaFreeHost(ctx->h_report);
     cudaFree(ctx->d_hist_pts); cudaFree(ctx->d_hist_ten); cudaFree(ctx->d_hist_err); cudaFree(ctx->d_hist_mask); cudaFree(ctx->d_hist_gr);
@@ -1199,6 +1200,48 @@ extern "C" int tpose_cuda_render(tpose_cuda_ctx* ctx, int raster_w, int raster_h
     ctx->launches += 2;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(rgba_host, colours, npix * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TPOSE_OK;
+}
+
+// A few instances on their own (see k_eval_list): entries = n x (v0, v1, v2, k).
+extern "C" int tpose_cuda_eval_list(tpose_cuda_ctx* ctx, int slot, const int32_t* entries_v0v1v2k, int n,
+                                    int32_t* ten_out, int32_t* cn_out, int32_t* ca_out_rgba)
+{
+    int rc = check_ready(ctx, slot, TPOSE_TRIANGULATE);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && !entries_v0v1v2k)) return fail(ctx, TPOSE_ERR_ARG, "eval_list: bad arguments");
+    if (n == 0) return TPOSE_OK;
+    ImageSlot& im = ctx->img[slot];
+    if (!im.table) return fail(ctx, TPOSE_ERR_STATE, "eval_list: needs the row-prefix table (contexts on the tile path do not keep one)");
+    for (int i = 0; i < n; i++) {
+        const int32_t* e = entries_v0v1v2k + 4 * (size_t)i;
+        if (e[0] < 0 || e[0] >= ctx->NP || e[1] < 0 || e[1] >= ctx->NP || e[2] < 0 || e[2] >= ctx->NP || e[3] < 0 || e[3] >= kVariants)
+            return fail(ctx, TPOSE_ERR_ARG, "eval_list: entry references a vertex outside [0,NP) or a variant outside [0,13)");
+    }
+    // scratch: entries (int4) | ten | cn | ca (int4), grow-only
+    const size_t need = (size_t)n * (sizeof(int4) * 2 + sizeof(int) * 2);
+    if (ctx->list_cap < need) {
+        cudaFree(ctx->list_buf); ctx->list_buf = nullptr; ctx->list_cap = 0;
+        CK(cudaMalloc((void**)&ctx->list_buf, need + need / 2));
+        ctx->list_cap = need + need / 2;
+    }
+    int4* d_en = (int4*)ctx->list_buf; int4* d_ca = d_en + n; int* d_ten = (int*)(d_ca + n); int* d_cn = d_ten + n;
+    const bool keep = ctx->run_cache_valid;
+    rc = upload_bytes(ctx, d_en, entries_v0v1v2k, sizeof(int4) * (size_t)n);
+    ctx->run_cache_valid = keep;                  // (nothing the cache mirrors changed)
+    if (rc) return rc;
+    const int blocks = (n + kListThreads / 32 - 1) / (kListThreads / 32);
+    const float dp = dp_for(ctx->NT, TPOSE_TRIANGULATE);
+    if (narrow_sums(im.W, im.H))
+        k_eval_list<unsigned><<<blocks, kListThreads, 0, ctx->stream>>>(im.table, im.pitch, im.W, im.H, ctx->pts, ctx->ratio, dp, d_en, n, d_ten, d_cn, d_ca);
+    else
+        k_eval_list<unsigned long long><<<blocks, kListThreads, 0, ctx->stream>>>(im.table, im.pitch, im.W, im.H, ctx->pts, ctx->ratio, dp, d_en, n, d_ten, d_cn, d_ca);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (ten_out) CK(cudaMemcpyAsync(ten_out, d_ten, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cn_out) CK(cudaMemcpyAsync(cn_out, d_cn, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ca_out_rgba) CK(cudaMemcpyAsync(ca_out_rgba, d_ca, sizeof(int4) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return TPOSE_OK;
 }

@@ -530,6 +530,66 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame)
     TL(1, 4);
 }
 
+// ---- k_eval_list -----------------------------------------------------------------------------------
+// A handful of instances evaluated on their own: entry i = (v0, v1, v2, k) -- three vertex indices into the
+// context's current points and a variant number k (0 = as it is, 1 + 4j + s = corner j moved, triangle.vs:66-78)
+// -- gives cn, ca and the mode-1 energy of that one instance with its own mean colour (triangle.fs:27-43,
+// triangulate flavour).  One warp per entry: the three sides are walked by all 32 lanes (rows interleaved)
+// over the row-prefix table, exactly like k_edges walks an edge.  This is what the flip set of a converged
+// frame needs (software/triangulate/main.cpp:287-306 re-rasterises all 13*NT instances twice to read the
+// base energies of the flipped pairs, then of all triangles): the instances are independent, so evaluating
+// just those gives the same numbers.
+constexpr int kListThreads = 256;
+
+template <typename ACC>
+__global__ void __launch_bounds__(kListThreads)
+k_eval_list(const uint4* __restrict__ table, int pitch, int W, int H, const float2* __restrict__ pts, float ratio, float dp,
+            const int4* __restrict__ entries, int n, int* __restrict__ ten, int* __restrict__ cn, int4* __restrict__ ca)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (kListThreads / 32) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int4 en = __ldg(entries + i);
+    const Xform xf{ratio, 0.5f * (float)W, 0.5f * (float)H, 256 * H};
+    const int vs[3] = {en.x, en.y, en.z};
+    int2 q[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        float dx = 0.0f, dy = 0.0f;
+        if (en.w > 0 && ((en.w - 1) >> 2) == j) fd_offset((en.w - 1) & 3, dp, dx, dy);
+        q[j] = to_fixed(pts[vs[j]], dx, dy, xf);
+    }
+    long long sr = 0, sg = 0, sb = 0, s2 = 0; int cnt = 0, odd = 0;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        EdgeWalk w;
+        w.init(q[j], q[(j + 1) % 3], H, lane, 32);
+        unsigned un = 0, uo = 0; ACC ur = 0, ug = 0, ub = 0; unsigned long long us2 = 0;
+        walk_edge<32, ACC>(w, table, pitch, W, un, uo, ur, ug, ub, us2);
+        const int sgn = w.sign;
+        cnt += sgn * (int)un; odd += sgn * (int)uo;
+        sr += sgn * (long long)ur; sg += sgn * (long long)ug; sb += sgn * (long long)ub; s2 += sgn * (long long)us2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o); odd += __shfl_xor_sync(0xffffffffu, odd, o);
+        sr += __shfl_xor_sync(0xffffffffu, sr, o); sg += __shfl_xor_sync(0xffffffffu, sg, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane != 0) return;
+    if (cnt < 0) { cnt = -cnt; odd = -odd; sr = -sr; sg = -sg; sb = -sb; s2 = -s2; }
+    cn[i] = cnt;
+    ca[i] = make_int4((int)sr, (int)sg, (int)sb, 0);
+    long long e = 0;
+    if (cnt > 0) {
+        int m0, m1, m2;                   // the mean colour exactly as eval_variant forms it
+        if (sr == (int)sr && sg == (int)sg && sb == (int)sb) { m0 = (int)sr / cnt; m1 = (int)sg / cnt; m2 = (int)sb / cnt; }
+        else { m0 = (int)(sr / cnt); m1 = (int)(sg / cnt); m2 = (int)(sb / cnt); }
+        e = energy_closed_form(cnt, odd, sr, sg, sb, s2, m0, m1, m2);
+    }
+    ten[i] = (int)(unsigned)(unsigned long long)e;
+}
+
 // un-fused gradient.cs / shift.cs, for the literal doshift() entry point
 // triangle.vs:93-98: only vertices some triangle references are reset
 __global__ void k_zero_gradient(int2* gr, int np, const int* __restrict__ corner_off)
