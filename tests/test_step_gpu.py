@@ -440,3 +440,40 @@ def test_frame_call_equals_upload_step_retrieve(cuda_pkg, synth, O):
     a.frame(0, cuda_pkg.TRIANGULATE, ten=ten, pts_out=out)
     assert np.array_equal(ten, ref["ten"]) and np.array_equal(bits(out), bits(ref["pts"]))
     a.close(); b.close()
+
+
+def test_eval_list_equals_rows_of_the_full_evaluation(cuda_pkg, synth, O, kernel_path):
+    """tpose_cuda_eval_list: instances evaluated on their own (the device half of the flip set,
+    triangulate/main.cpp:287-306) give the rows the full 13*NT evaluation holds for them -- also for
+    triangles that are not part of the uploaded mesh (a flipped pair)."""
+    if kernel_path == "tiles":
+        pytest.skip("eval_list walks the row-prefix table")
+    w, h = 320, 200
+    ratio = w / h
+    img = synth.make_image(w, h, seed=14)
+    pts, tri, he = synth.mesh_for(1000, ratio)
+    NT = tri.shape[0]
+    ctx = _ctx(cuda_pkg)
+    ctx.set_image(0, img)
+    ctx.upload(pts, tri, ratio)
+    ref = O.step(img, pts, tri, ratio, O.TRIANGULATE)
+    rng = np.random.default_rng(0)
+    en = np.concatenate([tri[:, :3], np.zeros((NT, 1), np.int32)], 1)               # every base row
+    extra = [(int(t), int(k)) for t, k in zip(rng.integers(0, NT, 40), rng.integers(1, 13, 40))]
+    en = np.concatenate([en, np.array([[*tri[t, :3], k] for t, k in extra], np.int32)])
+    ten, cn, ca = ctx.eval_list(0, en)
+    assert np.array_equal(ten[:NT], ref["ten"][:NT]) and np.array_equal(cn[:NT], ref["cn"][:NT])
+    assert np.array_equal(ca[:NT, :3], ref["ca"][:NT, :3])
+    for i, (t, k) in enumerate(extra):
+        g = k * NT + t
+        assert ten[NT + i] == ref["ten"][g] and cn[NT + i] == ref["cn"][g] and np.array_equal(ca[NT + i, :3], ref["ca"][g, :3])
+    # a flipped pair: triangles (a, b, c) + (c, b, d) -> (a, b, d) + (a, d, c); compare with a mesh that holds them
+    t0 = 2 * 37
+    a, b, c = tri[t0, :3]; d = tri[t0 + 1, 2]
+    tri2 = tri.copy(); tri2[t0, :3] = (a, b, d); tri2[t0 + 1, :3] = (a, d, c)
+    ref2 = O.step(img, pts, tri2, ratio, O.TRIANGULATE)
+    ten2, cn2, _ = ctx.eval_list(0, np.array([[a, b, d, 0], [a, d, c, 0]], np.int32))
+    assert np.array_equal(ten2, ref2["ten"][[t0, t0 + 1]]) and np.array_equal(cn2, ref2["cn"][[t0, t0 + 1]])
+    with pytest.raises(cuda_pkg.TposeCudaError):
+        ctx.eval_list(0, np.array([[0, 1, 99999, 0]], np.int32))
+    ctx.close()
