@@ -195,10 +195,12 @@ int tpose_cuda_watch_mask(tpose_cuda_ctx *ctx, uint32_t *mask_words, int nwords)
  * vertex indices and a variant number k (0 = the triangle as it is, 1 + 4j + s = corner j moved by +-dp like
  * triangle.vs:66-78; dp from the uploaded NT) -- yields what the full triangulate-flavour evaluation would put
  * in row k of a triangle with those vertices: cn (fragment count), ca (colour sums), ten (energy against the
- * instance's own mean colour, triangle.fs:27-43).  Nothing of the context's SSBOs is touched.  This is the
+ * instance's own mean colour, triangle.fs:27-43).  Of the context's SSBOs only pgradbuf is touched, and only
+ * with reset_gradient != 0: the mode-1 draw this call stands in for zeroes it for every vertex the uploaded
+ * mesh references (triangle.vs:93-98), which is visible later if an edit leaves such a vertex unreferenced.  This is the
  * device half of the flip set of a converged frame (software/triangulate/main.cpp:287-306 re-rasterises all
  * 13*NT instances twice to read a few base energies).  Needs the table path.  Outputs may be NULL. */
-int tpose_cuda_eval_list(tpose_cuda_ctx *ctx, int slot, const int32_t *entries_v0v1v2k, int n,
+int tpose_cuda_eval_list(tpose_cuda_ctx *ctx, int slot, const int32_t *entries_v0v1v2k, int n, int reset_gradient,
                          int32_t *ten_out, int32_t *cn_out, int32_t *ca_out_rgba);
 
 /* ---- batches of independent jobs --------------------------------------------
@@ -311,6 +313,23 @@ int tpose_cuda_host_alloc(size_t bytes, void **out);
 int tpose_cuda_host_free(void *p);
 /* Writes `bytes` of device scratch owned by the context (benchmark hygiene: evicts L2). */
 int tpose_cuda_flush_l2(tpose_cuda_ctx *ctx, size_t bytes);
+
+/* ---- software/rgbd: plane-fit meshing core (rgbd/main.cpp:244-349) ----------------------------------------
+ * For every triangle of a triangulation (mesh coordinates pts_xy): the depth points whose colour-image pixel
+ * (pixels_xy) lies inside the triangle's pixel-space bounding box and strictly inside the triangle (tpose::
+ * intriangle after TB) give a plane -- mean of points_xyzw.xyz, normalised mean of normals_xyzw.xyz, summed in
+ * index order like the reference's std::set loop; the triangle's three corners (T * p) are un-projected onto
+ * it and every vertex becomes the average of the corners its triangles produced (verts_xyzw, np vec4; a vertex
+ * with no such triangle is 0/0 = NaN, as coded).  T9 / TB9: the reference's mat3 T and inverse(T)
+ * (rgbd/main.cpp:94-99), column-major.  The library piolib the reference leans on is unreleased; its helpers
+ * are restated as a pinhole model: project(p) = (fx p.x/p.z + ppx, fy p.y/p.z + ppy), unproject = the ray
+ * through the pixel intersected with the plane.  ring (np floats) / tri_counts (nt ints, points gathered per
+ * triangle) may be NULL.  The reference's brute-force host loop is O(nt * npoints); here one block per
+ * triangle scans the points. */
+int tpose_cuda_rgbd_planefit(int device, const int32_t *tri_xyzw, int nt, const float *pts_xy, int np,
+                             const float *T9, const float *TB9, const float *pixels_xy, const float *points_xyzw,
+                             const float *normals_xyzw, int npoints, const float *intr_fx_fy_ppx_ppy,
+                             float *verts_xyzw, float *ring, int32_t *tri_counts);
 
 #ifdef __cplusplus
 }

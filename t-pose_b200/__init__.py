@@ -43,7 +43,7 @@ EXPORTS = [
     "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
     "tpose_cuda_raster_ids", "tpose_cuda_render", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_last_setup_ms", "tpose_cuda_kernel_path", "tpose_cuda_set_kernel_timing", "tpose_cuda_set_step_scale", "tpose_cuda_sync",
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
-    "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_select_matches", "tpose_cuda_carry", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
+    "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_rgbd_planefit", "tpose_cuda_select_matches", "tpose_cuda_carry", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
     "tpose_cuda_mview_last_ms",
     "tpose_cuda_watch", "tpose_cuda_watch_mask", "tpose_cuda_set_history", "tpose_cuda_eval_list", "tpose_cuda_history_frame", "tpose_cuda_history_restore_gradient", "tpose_cuda_read", "tpose_cuda_write", "tpose_cuda_batch_step", "tpose_cuda_batch_run",
 ]
@@ -175,12 +175,12 @@ class Context:
         self._ck(lib().tpose_cuda_history_frame(self._h, C.c_int(frame), _ptr(pts), _ptr(m), nw, _ptr(ten), C.byref(tot)))
         return dict(pts=pts, mask=np.unpackbits(m.view(np.uint8), bitorder="little")[:self.NT].astype(bool), ten=ten, toterr=tot.value)
 
-    def eval_list(self, slot, entries):
+    def eval_list(self, slot, entries, reset_gradient=False):
         """entries (n, 4) int32 = (v0, v1, v2, k): (ten, cn, ca) of those instances at the current points."""
         en = np.ascontiguousarray(entries, np.int32).reshape(-1, 4)
         n = en.shape[0]
         ten = np.zeros(n, np.int32); cn = np.zeros(n, np.int32); ca = np.zeros((n, 4), np.int32)
-        self._ck(lib().tpose_cuda_eval_list(self._h, slot, _ptr(en), n, _ptr(ten), _ptr(cn), _ptr(ca)))
+        self._ck(lib().tpose_cuda_eval_list(self._h, slot, _ptr(en), n, int(reset_gradient), _ptr(ten), _ptr(cn), _ptr(ca)))
         return ten, cn, ca
 
     def history_restore_gradient(self, frame):
@@ -391,6 +391,20 @@ def carry(tri, frm, to, pts, ratio, device=0):
     _mview_ck(lib().tpose_cuda_carry(device, _ptr(tri), tri.shape[0], _ptr(frm), _ptr(to), frm.shape[0], _ptr(out),
                                      out.shape[0], C.c_float(ratio)), "carry")
     return out
+
+
+def rgbd_planefit(tri, pts, T, TB, pixels, points, normals, intr, device=0):
+    """software/rgbd's meshing core (rgbd/main.cpp:244-349): (vertices (NP,4), ring (NP,), points per triangle (NT,)).
+    T / TB: 3x3 as m[col][row] (glm layout)."""
+    tri = np.ascontiguousarray(tri, np.int32); pts = np.ascontiguousarray(pts, np.float32)
+    T = np.ascontiguousarray(T, np.float32).reshape(9); TB = np.ascontiguousarray(TB, np.float32).reshape(9)
+    px = np.ascontiguousarray(pixels, np.float32).reshape(-1, 2); X = np.ascontiguousarray(points, np.float32).reshape(-1, 4)
+    N = np.ascontiguousarray(normals, np.float32).reshape(-1, 4); k = np.ascontiguousarray(intr, np.float32).reshape(4)
+    V = np.zeros((pts.shape[0], 4), np.float32); ring = np.zeros(pts.shape[0], np.float32); cnt = np.zeros(tri.shape[0], np.int32)
+    _mview_ck(lib().tpose_cuda_rgbd_planefit(device, _ptr(tri), tri.shape[0], _ptr(pts), pts.shape[0], _ptr(T), _ptr(TB),
+                                             _ptr(px) if len(px) else None, _ptr(X) if len(px) else None, _ptr(N) if len(px) else None,
+                                             len(px), _ptr(k), _ptr(V), _ptr(ring), _ptr(cnt)), "rgbd_planefit")
+    return V, ring, cnt
 
 
 def mview_last_ms():

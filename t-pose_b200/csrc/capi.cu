@@ -6,6 +6,7 @@
 #include "eval.cuh"
 #include "mview.cuh"
 #include "raster.cuh"
+#include "rgbd.cuh"
 #include "table.cuh"
 #include "tiles.cuh"
 
@@ -1205,15 +1206,22 @@ extern "C" int tpose_cuda_render(tpose_cuda_ctx* ctx, int raster_w, int raster_h
 }
 
 // A few instances on their own (see k_eval_list): entries = n x (v0, v1, v2, k).
-extern "C" int tpose_cuda_eval_list(tpose_cuda_ctx* ctx, int slot, const int32_t* entries_v0v1v2k, int n,
+extern "C" int tpose_cuda_eval_list(tpose_cuda_ctx* ctx, int slot, const int32_t* entries_v0v1v2k, int n, int reset_gradient,
                                     int32_t* ten_out, int32_t* cn_out, int32_t* ca_out_rgba)
 {
     int rc = check_ready(ctx, slot, TPOSE_TRIANGULATE);
     if (rc) return rc;
     if (n < 0 || (n > 0 && !entries_v0v1v2k)) return fail(ctx, TPOSE_ERR_ARG, "eval_list: bad arguments");
-    if (n == 0) return TPOSE_OK;
     ImageSlot& im = ctx->img[slot];
     if (!im.table) return fail(ctx, TPOSE_ERR_STATE, "eval_list: needs the row-prefix table (contexts on the tile path do not keep one)");
+    if (reset_gradient) {
+        // the mode-1 draw this call stands in for resets pgradbuf of every referenced vertex (triangle.vs:93-98)
+        if ((rc = rebuild_edges(ctx)) != 0) return rc;
+        k_zero_gradient<<<(ctx->NP + 255) / 256, 256, 0, ctx->stream>>>(ctx->gr, ctx->NP, ctx->corner_off);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (n == 0) return TPOSE_OK;
     for (int i = 0; i < n; i++) {
         const int32_t* e = entries_v0v1v2k + 4 * (size_t)i;
         if (e[0] < 0 || e[0] >= ctx->NP || e[1] < 0 || e[1] >= ctx->NP || e[2] < 0 || e[2] >= ctx->NP || e[3] < 0 || e[3] >= kVariants)
@@ -1595,5 +1603,48 @@ extern "C" int tpose_cuda_hdlt(int device, const float* PA12, const float* PB12,
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(X4_out, dX, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
     MCK(cudaStreamSynchronize(st));
+    return TPOSE_OK;
+}
+
+// ---- software/rgbd's plane-fit meshing core (rgbd/main.cpp:244-349) ------------------------------------------
+extern "C" int tpose_cuda_rgbd_planefit(int device, const int32_t* tri_xyzw, int nt, const float* pts_xy, int np,
+                                        const float* T9, const float* TB9, const float* pixels_xy, const float* points_xyzw,
+                                        const float* normals_xyzw, int npoints, const float* intr_fx_fy_ppx_ppy,
+                                        float* verts_xyzw, float* ring, int32_t* tri_counts)
+{
+    if (!tri_xyzw || !pts_xy || !T9 || !TB9 || !intr_fx_fy_ppx_ppy || !verts_xyzw || nt < 1 || np < 3 || npoints < 0 ||
+        (npoints > 0 && (!pixels_xy || !points_xyzw || !normals_xyzw)))
+        return mview_fail(TPOSE_ERR_ARG, "rgbd_planefit: bad arguments");
+    for (int t = 0; t < nt; t++)
+        for (int k = 0; k < 3; k++)
+            if (tri_xyzw[4 * t + k] < 0 || tri_xyzw[4 * t + k] >= np) return mview_fail(TPOSE_ERR_ARG, "rgbd_planefit: triangle references a vertex outside [0,np)");
+    MviewWs* ws = nullptr;
+    const size_t npt = (size_t)std::max(npoints, 1);
+    int rc = mview_workspace(device, padded(sizeof(int4) * nt) + padded(sizeof(float2) * np) + padded(sizeof(float2) * npt) + 2 * padded(sizeof(float4) * npt) +
+                                         padded(sizeof(float4) * 3 * nt) + 2 * padded(sizeof(int) * nt) + padded(sizeof(float4) * np) + padded(sizeof(float) * np) + 4096, &ws);
+    if (rc) return rc;
+    int4* dT = carve<int4>(ws, nt); float2* dP = carve<float2>(ws, np); float2* dPx = carve<float2>(ws, npt);
+    float4* dX = carve<float4>(ws, npt); float4* dN = carve<float4>(ws, npt); float4* dC = carve<float4>(ws, 3 * (size_t)nt);
+    int* dHas = carve<int>(ws, nt); int* dCnt = carve<int>(ws, nt); float4* dV = carve<float4>(ws, np); float* dR = carve<float>(ws, np);
+    cudaStream_t st = ws->stream;
+    MCK(cudaMemcpyAsync(dT, tri_xyzw, sizeof(int4) * nt, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dP, pts_xy, sizeof(float2) * np, cudaMemcpyHostToDevice, st));
+    if (npoints > 0) {
+        MCK(cudaMemcpyAsync(dPx, pixels_xy, sizeof(float2) * npoints, cudaMemcpyHostToDevice, st));
+        MCK(cudaMemcpyAsync(dX, points_xyzw, sizeof(float4) * npoints, cudaMemcpyHostToDevice, st));
+        MCK(cudaMemcpyAsync(dN, normals_xyzw, sizeof(float4) * npoints, cudaMemcpyHostToDevice, st));
+    }
+    RgbdMap map; RgbdIntr intr{intr_fx_fy_ppx_ppy[0], intr_fx_fy_ppx_ppy[1], intr_fx_fy_ppx_ppy[2], intr_fx_fy_ppx_ppy[3]};
+    memcpy(map.T, T9, sizeof map.T); memcpy(map.TB, TB9, sizeof map.TB);
+    MCK(cudaEventRecord(ws->e0, st));
+    k_rgbd_fit<<<nt, kRgbdThreads, 0, st>>>(dT, nt, dP, map, dPx, dX, dN, npoints, intr, dC, dHas, dCnt);
+    k_rgbd_gather<<<(np + 127) / 128, 128, 0, st>>>(dT, nt, np, dC, dHas, dV, dR);
+    MCK(cudaEventRecord(ws->e1, st));
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpyAsync(verts_xyzw, dV, sizeof(float4) * np, cudaMemcpyDeviceToHost, st));
+    if (ring) MCK(cudaMemcpyAsync(ring, dR, sizeof(float) * np, cudaMemcpyDeviceToHost, st));
+    if (tri_counts) MCK(cudaMemcpyAsync(tri_counts, dCnt, sizeof(int) * nt, cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&g_mview_ms, ws->e0, ws->e1);
     return TPOSE_OK;
 }
