@@ -240,6 +240,11 @@ int tpose_cuda_raster_ids(tpose_cuda_ctx *ctx, int slot, int32_t *ids_host);
  * NULL for s = 0.  Same raster conventions as the step; rgba_host: raster_h*raster_w*4 bytes. */
 int tpose_cuda_render(tpose_cuda_ctx *ctx, int raster_w, int raster_h, const float *other_pts_xy, float s,
                       uint8_t *rgba_host);
+/* The same picture with the viewer's wireframe on top (its `n` key; view/main.cpp:58-69,112-121 and
+ * view/shader/linestrip.{vs,fs}): the three sides of every triangle as one-pixel white lines.  Line fragments
+ * follow the written-down convention of csrc/raster.cuh (GL leaves them to the driver). */
+int tpose_cuda_render_wire(tpose_cuda_ctx *ctx, int raster_w, int raster_h, const float *other_pts_xy, float s,
+                           uint8_t *rgba_host);
 
 /* Device time in milliseconds of the most recent step/run call on this
  * context, measured with CUDA events on the context's stream. */

@@ -152,3 +152,32 @@ def step(rgba, pts, tri, ratio, flavour, colors=None, gr=None):
     gr = gradient(tri, ten, gr)
     new_pts = shift(pts, gr[:_f32(pts).shape[0]], ratio, flavour)
     return dict(cn=cn, ca=ca, ten=ten, gr=gr, pts=new_pts)
+
+
+def wire_pixels(pts, tri, ratio, W, H):
+    """Wireframe fragments under the convention of csrc/raster.cuh::k_wire (GL leaves line fragments to the
+    driver): boolean (H, W) mask of the pixels the three sides of every triangle light up."""
+    V = variant_vertices(pts, tri, ratio, W, H, TRIANGULATE)[:_i32(tri).shape[0]].astype(np.int64)     # base instances: snapped corners
+    mask = np.zeros((H, W), bool)
+    for t in range(V.shape[0]):
+        for k in range(3):
+            (ax, ay), (bx, by) = V[t, k], V[t, (k + 1) % 3]
+            dx, dy = bx - ax, by - ay
+            if dx == 0 and dy == 0:
+                continue
+            xmajor = abs(dx) >= abs(dy)
+            ua, va, ub, vb = (ax, ay, bx, by) if xmajor else (ay, ax, by, bx)
+            if ua > ub:
+                ua, va, ub, vb = ub, vb, ua, va
+            du, dv = ub - ua, vb - va
+            ulim, vlim = (W, H) if xmajor else (H, W)
+            c0, c1 = max((ua - 128 + 255) >> 8, 0), min((ub - 128 + 255) >> 8, ulim)
+            for c in range(int(c0), int(c1)):
+                m = 256 * c + 128 - ua
+                r = (va + (dv * m) // du) >> 8
+                if 0 <= r < vlim:
+                    if xmajor:
+                        mask[r, c] = True
+                    else:
+                        mask[c, r] = True
+    return mask

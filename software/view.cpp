@@ -1,7 +1,8 @@
 // software/view, headless: draws every level of a .tri stack as flat-coloured triangles (what the
 // reference's viewer shows in its window, view/main.cpp:104-121) and writes one PPM per level.
 //
-//   view -t mesh.tri [-o prefix] [-height 600] [-s 0.0] [-device D]
+//   view -t mesh.tri [-o prefix] [-height 600] [-s 0.0] [-n] [-device D]
+//     -n         wireframe on top (the viewer's `n` key, view/main.cpp:58-69)
 //     -height H  raster height; the width is RATIO*H like the reference's window (view/main.cpp:44)
 //     -s S       interpolation between points (0) and originpoints (1), the viewer's animated `s`
 #include <tpose/tpose>
@@ -27,7 +28,7 @@ int main(int argc, char* args[])
         const int W = (int)(tpose::RATIO * H);                                   // view/main.cpp:44
         tpose::upload(&tr);                                                      // colours into tcolaccbuf
         std::vector<unsigned char> rgba((size_t)W * H * 4);
-        tpose::check(tpose_cuda_render(tpose::context, W, H, &tr.originpoints[0].x, s, rgba.data()), "render");
+        tpose::check((has_flag(argc, args, "n") ? tpose_cuda_render_wire : tpose_cuda_render)(tpose::context, W, H, &tr.originpoints[0].x, s, rgba.data()), "render");
         const std::string out = prefix + "." + std::to_string(level++) + ".ppm";
         FILE* f = fopen(out.c_str(), "wb");
         if (!f) { std::cout << "cannot write " << out << std::endl; return 1; }

@@ -41,7 +41,7 @@ EXPORTS = [
     "tpose_cuda_upload_points", "tpose_cuda_colors", "tpose_cuda_energy", "tpose_cuda_shift",
     "tpose_cuda_step", "tpose_cuda_frame", "tpose_cuda_run", "tpose_cuda_set_toterr", "tpose_cuda_get_toterr",
     "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
-    "tpose_cuda_raster_ids", "tpose_cuda_render", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_last_setup_ms", "tpose_cuda_kernel_path", "tpose_cuda_set_kernel_timing", "tpose_cuda_set_step_scale", "tpose_cuda_sync",
+    "tpose_cuda_raster_ids", "tpose_cuda_render", "tpose_cuda_render_wire", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_last_setup_ms", "tpose_cuda_kernel_path", "tpose_cuda_set_kernel_timing", "tpose_cuda_set_step_scale", "tpose_cuda_sync",
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
     "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_rgbd_planefit", "tpose_cuda_select_matches", "tpose_cuda_carry", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
     "tpose_cuda_mview_last_ms",
@@ -237,11 +237,12 @@ class Context:
         self._ck(lib().tpose_cuda_raster_ids(self._h, slot, _ptr(ids)))
         return ids
 
-    def render(self, w, h, other_pts=None, s=0.0):
-        """software/view, headless: (h, w, 4) uint8, flat triangle colours on black."""
+    def render(self, w, h, other_pts=None, s=0.0, lines=False):
+        """software/view, headless: (h, w, 4) uint8, flat triangle colours on black; lines: the wireframe on top."""
         out = np.empty((h, w, 4), np.uint8)
         op = None if other_pts is None else np.ascontiguousarray(other_pts, np.float32)
-        self._ck(lib().tpose_cuda_render(self._h, w, h, _ptr(op), C.c_float(s), _ptr(out)))
+        fn = lib().tpose_cuda_render_wire if lines else lib().tpose_cuda_render
+        self._ck(fn(self._h, w, h, _ptr(op), C.c_float(s), _ptr(out)))
         return out
 
     def last_elapsed_ms(self):

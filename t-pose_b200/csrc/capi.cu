@@ -1172,7 +1172,20 @@ extern "C" int tpose_cuda_raster_ids(tpose_cuda_ctx* ctx, int slot, int32_t* ids
     return TPOSE_OK;
 }
 
+static int render_common(tpose_cuda_ctx* ctx, int raster_w, int raster_h, const float* other_pts_xy, float s, int lines, uint8_t* rgba_host);
+
 extern "C" int tpose_cuda_render(tpose_cuda_ctx* ctx, int raster_w, int raster_h, const float* other_pts_xy, float s, uint8_t* rgba_host)
+{
+    return render_common(ctx, raster_w, raster_h, other_pts_xy, s, 0, rgba_host);
+}
+
+// the viewer with its `n` key down (view/main.cpp:58-69,112-121): the triangles' outlines in white on top
+extern "C" int tpose_cuda_render_wire(tpose_cuda_ctx* ctx, int raster_w, int raster_h, const float* other_pts_xy, float s, uint8_t* rgba_host)
+{
+    return render_common(ctx, raster_w, raster_h, other_pts_xy, s, 1, rgba_host);
+}
+
+static int render_common(tpose_cuda_ctx* ctx, int raster_w, int raster_h, const float* other_pts_xy, float s, int lines, uint8_t* rgba_host)
 {
     if (!ctx) return TPOSE_ERR_ARG;
     if (!ctx->have_mesh) return fail(ctx, TPOSE_ERR_STATE, "render: no mesh uploaded");
@@ -1199,6 +1212,10 @@ extern "C" int tpose_cuda_render(tpose_cuda_ctx* ctx, int raster_w, int raster_h
         pos, ctx->tri, ctx->NT, ctx->ratio, raster_w, raster_h, ctx->ids);
     k_flat_colors<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(ctx->ids, ctx->ca[ctx->cur], (int)npix, colours);
     ctx->launches += 2;
+    if (lines) {
+        k_wire<<<(3 * ctx->NT + 127) / 128, 128, 0, ctx->stream>>>(pos, ctx->tri, ctx->NT, ctx->ratio, raster_w, raster_h, colours);
+        ctx->launches++;
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(rgba_host, colours, npix * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

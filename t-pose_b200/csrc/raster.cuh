@@ -70,4 +70,39 @@ __global__ void k_flat_colors(const int* __restrict__ ids, const int4* __restric
     out[i] = c;
 }
 
+// The viewer's wireframe (view/main.cpp:58-69,112-121: GL_LINE_STRIP over the corners of every triangle, white,
+// view/shader/linestrip.fs).  GL leaves the exact fragments of a line to the driver (diamond-exit rule "or
+// equivalent"); the convention here, shared with the oracle: end points snapped like the triangles' (1/256 px), a
+// line is x-major if |dx| >= |dy|; an x-major line produces one fragment in every pixel column whose centre
+// x lies in [min x, max x) -- in the row that holds the line's exact height at that centre -- and a y-major
+// line the same with the axes swapped.  Zero-length lines draw nothing.  One thread per (triangle, side).
+__global__ void k_wire(const float2* __restrict__ pts, const int4* __restrict__ tri, int NT, float ratio, int W, int H,
+                       uchar4* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * NT) return;
+    const int4 tv = tri[i / 3];
+    const int k = i % 3;
+    const int va = k == 0 ? tv.x : (k == 1 ? tv.y : tv.z), vb = k == 0 ? tv.y : (k == 1 ? tv.z : tv.x);
+    Xform xf{ratio, 0.5f * (float)W, 0.5f * (float)H, 256 * H};
+    int2 a = to_fixed(pts[va], 0.0f, 0.0f, xf), b = to_fixed(pts[vb], 0.0f, 0.0f, xf);
+    const long long dx = (long long)b.x - a.x, dy = (long long)b.y - a.y;
+    if (dx == 0 && dy == 0) return;
+    const bool xmajor = llabs(dx) >= llabs(dy);
+    // u = major axis, v = minor axis
+    long long ua = xmajor ? a.x : a.y, va2 = xmajor ? a.y : a.x, ub = xmajor ? b.x : b.y, vb2 = xmajor ? b.y : b.x;
+    if (ua > ub) { long long t = ua; ua = ub; ub = t; t = va2; va2 = vb2; vb2 = t; }
+    const long long du = ub - ua, dv = vb2 - va2;
+    const int ulim = xmajor ? W : H, vlim = xmajor ? H : W;
+    int c0 = (int)max((ua - 128 + 255) >> 8, 0ll), c1 = (int)min((ub - 128 + 255) >> 8, (long long)ulim);   // centres in [ua, ub)
+    for (int c = c0; c < c1; c++) {
+        const long long m = 256ll * c + 128 - ua;                     // 0 <= m < du
+        const long long v = va2 + floordiv64(dv * m, du);             // exact height (1/256 px) at the centre, rounded down
+        const long long r = v >> 8;
+        if (r < 0 || r >= vlim) continue;
+        const int x = xmajor ? c : (int)r, y = xmajor ? (int)r : c;
+        out[(size_t)y * W + x] = make_uchar4(255, 255, 255, 255);
+    }
+}
+
 }  // namespace tpose_dev

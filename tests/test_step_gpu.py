@@ -317,6 +317,11 @@ def test_headless_view_matches_the_id_raster(cuda_pkg, synth, O):
         want[drawn, :3] = np.clip(colors[ids[drawn], :3], 0, 255).astype(np.uint8)
         assert np.array_equal(got, want), (s, int((got != want).any(axis=2).sum()))
     assert np.array_equal(c.render(w, h), c.render(w, h, other, 0.0))
+    # the viewer's wireframe (`n` key): white one-pixel outlines on top of the same picture
+    plain, wired = c.render(w, h), c.render(w, h, lines=True)
+    wm = O.wire_pixels(pts, tri, ratio, w, h)
+    assert wm.sum() > 2 * (w + h)
+    assert (wired[wm] == 255).all() and np.array_equal(wired[~wm], plain[~wm])
     c.close()
 
 
