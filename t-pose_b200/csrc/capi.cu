@@ -31,6 +31,8 @@ constexpr int kTileH = 64;
 // a sequence of evaluations (see issue_sequence) and its instantiated graph
 struct SeqKey { const EvalJob* jobs; int njobs; EvalShape shape; int kind, len, first_set; unsigned flags; double tol; };
 struct SeqGraph { SeqKey key; cudaGraphExec_t exec; uint64_t stamp; };
+// one instantiated frame (tpose_cuda_frame with device-visible caller buffers: see frame_mapped)
+struct FrameGraph { const void* in; void* ten; void* cn; void* ca; void* out; int set, nt, np, slot, flavour; EvalShape shape; const EvalJob* job; cudaGraphExec_t exec; };
 
 struct ImageSlot {
     uchar4* rgba = nullptr;    // raster-resolution image on the device, rows ipitch pixels apart
@@ -99,6 +101,7 @@ struct tpose_cuda_ctx {
     int64_t launches = 0;
     int group = 0;                    // lanes per edge (0 = pick from NT and H)
     std::vector<SeqGraph> graphs; uint64_t graph_clock = 0; bool use_graphs = true;
+    std::vector<FrameGraph> frame_graphs;      // tpose_cuda_frame with pinned caller buffers
     bool mid_valid = false, time_kernels = false;
     // read-back cache filled by tpose_cuda_run in the same synchronisation as its verdict: the points and
     // toterr as the run left them (what the caller's next Buffer::retrieve / get_toterr would fetch)
@@ -258,6 +261,7 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+    for (auto& g : ctx->frame_graphs) cudaGraphExecDestroy(g.exec);
     for (auto& s : ctx->img) { cudaFree(s.rgba); cudaFree(s.table); cudaFree(s.coarse); cudaFree(s.tmap); }
     cudaFree(ctx->esnap); cudaFree(ctx->ebox); cudaFree(ctx->gbox);
     for (int s = 0; s < 2; s++) { cudaFree(ctx->cn[s]); cudaFree(ctx->ca[s]); cudaFree(ctx->ten[s]); }
@@ -763,6 +767,93 @@ extern "C" int tpose_cuda_step(tpose_cuda_ctx* ctx, int slot, int flavour, int n
 
 // Launch j evaluates the points after j shifts into set (first+j)&1 and carries the checks of frame
 // j-1; launch max_steps is check-only.  See eval.cuh.
+// ---- the frame's host traffic without DMA operations --------------------------------------------------
+// Page-locked host memory is visible to the device (unified addressing), so when the caller's frame buffers
+// are pinned the frame becomes ONE graph: a kernel that pulls the points in over PCIe, the step, and a kernel
+// that pushes ten | cn | ca | points out with coalesced 16-byte stores -- no copy-engine operation (each
+// costs microseconds of fixed latency, and a frame has four), one stream synchronisation.
+__global__ void k_frame_in(const float2* __restrict__ host_pts, float2* __restrict__ pts, int np)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) pts[i] = host_pts[i];
+}
+
+struct FrameOut { const int* ten; const int* cn; const int4* ca; const float2* pts; int* h_ten; int* h_cn; int4* h_ca; float2* h_pts; int nv, np; };
+
+__device__ __forceinline__ void copy_words(const int* __restrict__ src, int* __restrict__ dst, int n, int tid, int nthreads)
+{
+    // 16-byte chunks where both sides allow it (cudaMalloc / cudaHostAlloc memory is at least 256-byte aligned)
+    const bool vec = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+    const int n4 = vec ? n >> 2 : 0;
+    for (int i = tid; i < n4; i += nthreads) reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(src)[i];
+    for (int i = 4 * n4 + tid; i < n; i += nthreads) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) k_frame_out(FrameOut f)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    if (f.h_ten) copy_words(f.ten, f.h_ten, f.nv, tid, nthreads);
+    if (f.h_cn) copy_words(f.cn, f.h_cn, f.nv, tid, nthreads);
+    if (f.h_ca) copy_words(reinterpret_cast<const int*>(f.ca), reinterpret_cast<int*>(f.h_ca), 4 * f.nv, tid, nthreads);
+    if (f.h_pts) copy_words(reinterpret_cast<const int*>(f.pts), reinterpret_cast<int*>(f.h_pts), 2 * f.np, tid, nthreads);
+}
+
+// the device-side alias of a host pointer if the memory is page-locked and mapped, else nullptr
+static void* device_alias(const void* host)
+{
+    if (!host) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return a.devicePointer;
+}
+
+
+static int frame_mapped(tpose_cuda_ctx* ctx, int slot, int flavour, const float* pts_in, int32_t* ten13, int32_t* cn13, int32_t* ca13, float* pts_out,
+                        bool* done)
+{
+    *done = false;
+    if (!ctx->use_graphs) return TPOSE_OK;
+    // every buffer the caller passed must be device-visible; remember the verdict per pointer set
+    void* d_in = device_alias(pts_in); void* d_ten = device_alias(ten13); void* d_cn = device_alias(cn13);
+    void* d_ca = device_alias(ca13); void* d_out = device_alias(pts_out);
+    if ((pts_in && !d_in) || (ten13 && !d_ten) || (cn13 && !d_cn) || (ca13 && !d_ca) || (pts_out && !d_out)) return TPOSE_OK;
+    int rc = sync_job(ctx, slot, flavour);
+    if (rc) return rc;
+    const int set = ctx->cur ^ 1;
+    const EvalShape sh = shape_of(ctx, slot);
+    FrameGraph* g = nullptr;
+    for (auto& c : ctx->frame_graphs)
+        if (c.in == d_in && c.ten == d_ten && c.cn == d_cn && c.ca == d_ca && c.out == d_out && c.set == set && c.nt == ctx->NT && c.np == ctx->NP &&
+            c.slot == slot && c.flavour == flavour && c.job == ctx->job_dev && c.shape.group == sh.group && c.shape.grid_e == sh.grid_e &&
+            c.shape.grid_t == sh.grid_t && c.shape.narrow == sh.narrow && c.shape.path == sh.path && c.shape.grid_s == sh.grid_s &&
+            c.shape.grid_tiles == sh.grid_tiles) g = &c;
+    if (!g) {
+        cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            if (d_in) k_frame_in<<<(ctx->NP + 255) / 256, 256, 0, ctx->stream>>>((const float2*)d_in, ctx->pts, ctx->NP);
+            launch_eval(sh, ctx->job_dev, 1, set, fused_flags(flavour), 0.0, -1, ctx->stream);
+            FrameOut f{ctx->ten[set], ctx->cn[set], ctx->ca[set], ctx->pts, (int*)d_ten, (int*)d_cn, (int4*)d_ca, (float2*)d_out, kVariants * ctx->NT, ctx->NP};
+            k_frame_out<<<64, 256, 0, ctx->stream>>>(f);
+            e = cudaStreamEndCapture(ctx->stream, &graph);
+        }
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return TPOSE_OK; }       // (stream under foreign capture etc.: take the copy path)
+        if (ctx->frame_graphs.size() >= 8) { cudaGraphExecDestroy(ctx->frame_graphs.front().exec); ctx->frame_graphs.erase(ctx->frame_graphs.begin()); }
+        ctx->frame_graphs.push_back(FrameGraph{d_in, d_ten, d_cn, d_ca, d_out, set, ctx->NT, ctx->NP, slot, flavour, sh, ctx->job_dev, exec});
+        g = &ctx->frame_graphs.back();
+    }
+    ctx->run_cache_valid = false; ctx->run_mask_valid = false; ctx->mid_valid = false;
+    CK(cudaGraphLaunch(g->exec, ctx->stream));
+    ctx->launches += launches_per_eval(sh) + (d_in ? 2 : 1);
+    ctx->cur = set;
+    CK(cudaStreamSynchronize(ctx->stream));
+    *done = true;
+    return TPOSE_OK;
+}
+
 // One frame of the reference's loop as a single call (triangulate/main.cpp:196-204, warp/main.cpp:220-229):
 // optional pointbuf->fill, doenergy + doshift (+ the colours of the pipeline), and the read-backs the
 // frame ends with -- one stream synchronisation in all.
@@ -771,6 +862,8 @@ extern "C" int tpose_cuda_frame(tpose_cuda_ctx* ctx, int slot, int flavour, cons
 {
     int rc = check_ready(ctx, slot, flavour);
     if (rc) return rc;
+    bool done = false;
+    if ((rc = frame_mapped(ctx, slot, flavour, pts_in_xy, ten13, cn13, ca13, pts_out_xy, &done)) != 0 || done) return rc;
     if (pts_in_xy && (rc = upload_bytes(ctx, ctx->pts, pts_in_xy, sizeof(float2) * ctx->NP)) != 0) return rc;
     if ((rc = sync_job(ctx, slot, flavour)) != 0) return rc;
     ctx->cur ^= 1;

@@ -418,8 +418,11 @@ def test_run_history_equals_stepping_frame_by_frame(cuda_pkg, synth, O):
     a.close(); b.close()
 
 
-def test_frame_call_equals_upload_step_retrieve(cuda_pkg, synth, O):
-    """tpose_cuda_frame = pointbuf fill + fused step + the frame's read-backs, in one call."""
+@pytest.mark.parametrize("pinned", [False, True])
+def test_frame_call_equals_upload_step_retrieve(cuda_pkg, synth, O, pinned):
+    """tpose_cuda_frame = pointbuf fill + fused step + the frame's read-backs, in one call.  With page-locked
+    caller buffers (pinned) the frame is one graph that moves the data with kernels over mapped memory; with
+    pageable ones it goes through the copy engine.  Same bytes either way."""
     w, h = 256, 160
     ratio = w / h
     img = synth.make_image(w, h, seed=9)
@@ -428,8 +431,9 @@ def test_frame_call_equals_upload_step_retrieve(cuda_pkg, synth, O):
     a, b = _ctx(cuda_pkg), _ctx(cuda_pkg)
     for c in (a, b):
         c.set_image(0, img); c.upload(pts, tri, ratio)
-    cur = pts.copy()
-    ten = np.empty(nv, np.int32); cn = np.empty(nv, np.int32); ca = np.empty((nv, 4), np.int32); out = np.empty_like(pts)
+    alloc = cuda_pkg.pinned_empty if pinned else (lambda shape, dt: np.empty(shape, dt))
+    cur = alloc(pts.shape, np.float32); cur[...] = pts
+    ten = alloc((nv,), np.int32); cn = alloc((nv,), np.int32); ca = alloc((nv, 4), np.int32); out = alloc(pts.shape, np.float32)
     for i in range(3):
         a.frame(0, cuda_pkg.TRIANGULATE, pts_in=cur if i else None, ten=ten, cn=cn, ca=ca, pts_out=out)
         if i:
@@ -438,7 +442,7 @@ def test_frame_call_equals_upload_step_retrieve(cuda_pkg, synth, O):
         r = b.retrieve()
         assert np.array_equal(ten, r["ten"]) and np.array_equal(cn, r["cn"]) and np.array_equal(ca, r["ca"])
         assert np.array_equal(bits(out), bits(r["pts"]))
-        cur = out.copy()
+        cur[...] = out
         cur[10] += np.float32(0.001)                      # the host edits a point between frames
     ref = O.step(img, pts, tri, ratio, O.TRIANGULATE)
     a.upload(pts, tri, ratio)
