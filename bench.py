@@ -446,15 +446,16 @@ def run_ours(args):
     hcn = pkg.pinned_empty((13 * NT,), np.int32)
     Ke = max(K, min(200, 10 * K))
     ctx.upload(pts, tri, ratio)
+    frame = ctx.bind_frame(0, pkg.TRIANGULATE, pts_in=hpts, ten=hten, cn=hcn, pts_out=hpts)      # tpose_cuda_frame, arguments bound once
     for _ in range(3):
-        ctx.frame(0, pkg.TRIANGULATE, pts_in=hpts, ten=hten, cn=hcn, pts_out=hpts)
+        frame()
     hpts[...] = pts
     barrier(ctx)
     t0 = time.perf_counter()
     ctx.set_image(0, himg)
     for _ in range(Ke):
-        # pointbuf->fill(points) + step + read-backs, returns after the copies have landed
-        ctx.frame(0, pkg.TRIANGULATE, pts_in=hpts, ten=hten, cn=hcn, pts_out=hpts)
+        # pointbuf->fill(points) + step + read-backs, returns after the data has landed in the host buffers
+        frame()
     ctx.sync()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     h2d = (img.nbytes / Ke) + pts.nbytes

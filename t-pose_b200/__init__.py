@@ -142,6 +142,19 @@ class Context:
         """One reference frame: optional pointbuf fill, step, read-backs into caller-owned arrays."""
         self._ck(lib().tpose_cuda_frame(self._h, slot, flavour, _ptr(pts_in), _ptr(ten), _ptr(cn), _ptr(ca), _ptr(pts_out)))
 
+    def bind_frame(self, slot, flavour, pts_in=None, ten=None, cn=None, ca=None, pts_out=None):
+        """frame() with its arguments converted once: returns a zero-argument callable for loops that reuse the
+        same buffers every frame (the arrays must stay alive)."""
+        fn, h = lib().tpose_cuda_frame, self._h
+        args = (h, C.c_int(slot), C.c_int(flavour), _ptr(pts_in), _ptr(ten), _ptr(cn), _ptr(ca), _ptr(pts_out))
+        keep = (pts_in, ten, cn, ca, pts_out)
+
+        def call(_keep=keep):
+            rc = fn(*args)
+            if rc != 0:
+                self._ck(rc)
+        return call
+
     def run(self, slot, flavour, max_steps, rel_tol):
         n, f, e = C.c_int(), C.c_uint32(), C.c_float()
         self._ck(lib().tpose_cuda_run(self._h, slot, flavour, max_steps, C.c_double(rel_tol),

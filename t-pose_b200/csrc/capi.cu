@@ -102,6 +102,7 @@ struct tpose_cuda_ctx {
     int group = 0;                    // lanes per edge (0 = pick from NT and H)
     std::vector<SeqGraph> graphs; uint64_t graph_clock = 0; bool use_graphs = true;
     std::vector<FrameGraph> frame_graphs;      // tpose_cuda_frame with pinned caller buffers
+    const void* frame_host[5] = {(const void*)1, nullptr, nullptr, nullptr, nullptr}; void* frame_alias[5] = {};   // last pointer set seen and its device aliases
     bool mid_valid = false, time_kernels = false;
     // read-back cache filled by tpose_cuda_run in the same synchronisation as its verdict: the points and
     // toterr as the run left them (what the caller's next Buffer::retrieve / get_toterr would fetch)
@@ -815,8 +816,13 @@ static int frame_mapped(tpose_cuda_ctx* ctx, int slot, int flavour, const float*
     *done = false;
     if (!ctx->use_graphs) return TPOSE_OK;
     // every buffer the caller passed must be device-visible; remember the verdict per pointer set
-    void* d_in = device_alias(pts_in); void* d_ten = device_alias(ten13); void* d_cn = device_alias(cn13);
-    void* d_ca = device_alias(ca13); void* d_out = device_alias(pts_out);
+    const void* host5[5] = {pts_in, ten13, cn13, ca13, pts_out};
+    if (memcmp(host5, ctx->frame_host, sizeof host5) != 0) {          // (the attribute queries are not free: once per pointer set)
+        for (int i = 0; i < 5; i++) ctx->frame_alias[i] = device_alias(host5[i]);
+        memcpy(ctx->frame_host, host5, sizeof host5);
+    }
+    void* d_in = ctx->frame_alias[0]; void* d_ten = ctx->frame_alias[1]; void* d_cn = ctx->frame_alias[2];
+    void* d_ca = ctx->frame_alias[3]; void* d_out = ctx->frame_alias[4];
     if ((pts_in && !d_in) || (ten13 && !d_ten) || (cn13 && !d_cn) || (ca13 && !d_ca) || (pts_out && !d_out)) return TPOSE_OK;
     int rc = sync_job(ctx, slot, flavour);
     if (rc) return rc;
