@@ -25,7 +25,7 @@ using namespace tpose_dev;
 // Launch geometry of one evaluation.  Grid sizes are quantised (power of two, at most one full
 // wave) and the kernels stride, so a captured sequence stays valid while the mesh grows.
 // path: 0 = row-prefix table gathers (k_edges), 1 = TMA-staged tiles (k_setup + k_tiles)
-struct EvalShape { int group, grid_e, grid_t; bool narrow; int path, grid_s, grid_tiles; int sub; };
+struct EvalShape { int group, grid_e, grid_t; bool narrow; int path, grid_s, grid_tiles; };
 constexpr int kPathTable = 0, kPathTiles = 1;
 constexpr int kTileH = 64;
 // a sequence of evaluations (see issue_sequence) and its instantiated graph
@@ -509,7 +509,7 @@ static EvalShape make_shape(int group, int max_np, int max_ne, bool narrow, int 
 {
     const int per_block = kEdgeThreads / group;
     EvalShape sh{group, quantised_grid(((long long)max_ne * kEdgeMoves + per_block - 1) / per_block),
-                 quantised_grid((max_np + kCornerWarps - 1) / kCornerWarps), narrow, path, 0, 0, 0};
+                 quantised_grid((max_np + kCornerWarps - 1) / kCornerWarps), narrow, path, 0, 0};
     if (path == kPathTiles) {
         // (group, grid_e and narrow do not exist on the tile path: keep them out of the graph key)
         sh.group = 1; sh.grid_e = 0; sh.narrow = true;
@@ -531,14 +531,6 @@ static void launch_edges(const EvalJob* jobs, int njobs, const EvalShape& sh, in
 static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int set, unsigned flags, double tol, int frame, cudaStream_t st,
                         cudaEvent_t mid = nullptr, cudaEvent_t mid0 = nullptr)
 {
-    // A large batch goes through in slices of sh.sub jobs, each slice's k_corners right behind its k_edges: the
-    // slice's edge records (2 MB per 1080p / 3000 job) are then still in L2 when k_corners reads them, instead of
-    // having been pushed out to HBM by the other jobs' table traffic.
-    if (sh.sub > 0 && njobs > sh.sub) {
-        EvalShape one = sh; one.sub = 0;
-        for (int j0 = 0; j0 < njobs; j0 += sh.sub) launch_eval(one, jobs + j0, std::min(sh.sub, njobs - j0), set, flags, tol, frame, st);
-        return;
-    }
     if (sh.path == kPathTiles) {
         k_setup<kTileH><<<dim3(sh.grid_s + 1, njobs), kSetupThreads, 0, st>>>(jobs, set, flags, tol, frame);   // + the service block
         if (mid0) cudaEventRecord(mid0, st);
@@ -558,11 +550,7 @@ static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int
     if (mid) cudaEventRecord(mid, st);
     k_corners<<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame);
 }
-static int launches_per_eval(const EvalShape& sh, int njobs = 1)
-{
-    const int slices = (sh.sub > 0 && njobs > sh.sub) ? (njobs + sh.sub - 1) / sh.sub : 1;
-    return slices * (sh.path == kPathTiles ? 3 : 2);
-}
+static int launches_per_eval(const EvalShape& sh) { return sh.path == kPathTiles ? 3 : 2; }
 
 // ---- sequences of evaluations, replayed as CUDA graphs ------------------------------------------
 // A sequence is `len` evaluations into alternating buffer sets starting at `first_set`.
@@ -591,13 +579,13 @@ static bool same_key(const SeqKey& a, const SeqKey& b)
     return a.jobs == b.jobs && a.njobs == b.njobs && a.kind == b.kind && a.len == b.len && a.first_set == b.first_set &&
            a.flags == b.flags && a.tol == b.tol && a.shape.group == b.shape.group && a.shape.grid_e == b.shape.grid_e &&
            a.shape.grid_t == b.shape.grid_t && a.shape.narrow == b.shape.narrow && a.shape.path == b.shape.path &&
-           a.shape.grid_s == b.shape.grid_s && a.shape.grid_tiles == b.shape.grid_tiles && a.shape.sub == b.shape.sub;
+           a.shape.grid_s == b.shape.grid_s && a.shape.grid_tiles == b.shape.grid_tiles;
 }
 
 static int issue_sequence(tpose_cuda_ctx* ctx, const SeqKey& key)
 {
     ctx->run_cache_valid = false; ctx->run_mask_valid = false;
-    ctx->launches += (int64_t)launches_per_eval(key.shape, key.njobs) * key.len;
+    ctx->launches += (int64_t)launches_per_eval(key.shape) * key.len;
     if (key.len < kGraphMinLen || !ctx->use_graphs || (key.len == 1 && ctx->time_kernels)) {
         const bool mid = key.len == 1 && ctx->time_kernels;
         issue_direct(key, ctx->stream, mid ? ctx->ev_mid : nullptr, mid ? ctx->ev_mid0 : nullptr);
@@ -1116,10 +1104,6 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
     CK(cudaMemcpyAsync(lead->batch_jobs, jobs.data(), sizeof(EvalJob) * n, cudaMemcpyHostToDevice, lead->stream));
     CK(cudaStreamSynchronize(lead->stream));   // `jobs` is a local
     *shape = make_shape(valid_group(lead->group) ? lead->group : group_for(rows / n, items), mxp, mxe, narrow, lead->path, mxt);
-    {   // slice size of a batch (see launch_eval); TPOSE_CUDA_SUBBATCH=0 switches slicing off
-        const char* sb = getenv("TPOSE_CUDA_SUBBATCH");
-        shape->sub = sb ? atoi(sb) : 16;
-    }
     return TPOSE_OK;
 }
 
