@@ -189,7 +189,8 @@ def shared_config(w, h, NT, NP, world):
     return {"workload": f"single {w}x{h} image per GPU, {NT} triangles ({NP} points), frozen topology, "
                         "triangulate flavour (BASELINE.json configs[1])",
             "raster": "native",
-            "l2": f"GPU arm: L2 flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB write); CPU arm: steps back to back",
+            "l2": f"GPU arm: L2 flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB written, then read back so that no dirty "
+                  "flush lines are left for the timed kernels to write out); CPU arm: steps back to back",
             "parallelism": f"replicas x{world}: one independent image per GPU"}
 
 

@@ -1459,12 +1459,30 @@ extern "C" int tpose_cuda_host_free(void* p)
     return cudaFreeHost(p) == cudaSuccess ? TPOSE_OK : TPOSE_ERR_CUDA;
 }
 
+// reads `n16` 16-byte words and keeps the compiler from dropping the loads
+__global__ void k_read_sink(const uint4* __restrict__ p, size_t n16, unsigned* sink)
+{
+    unsigned acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldcs(p + i);
+        acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+
+// Measurement aid: evicts everything the context's kernels could find in L2.  A buffer larger than L2 is
+// written and then read back: after the write alone L2 would be full of DIRTY lines of the flush buffer, and
+// the timed kernel would pay their write-back on every miss -- an artefact of the flush, not of the workload.
+// After the read pass L2 holds clean lines of the buffer's tail.
 extern "C" int tpose_cuda_flush_l2(tpose_cuda_ctx* ctx, size_t bytes)
 {
     if (!ctx || bytes == 0) return TPOSE_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    if (ctx->flush_cap < bytes) { cudaFree(ctx->flush); ctx->flush = nullptr; CK(cudaMalloc((void**)&ctx->flush, bytes)); ctx->flush_cap = bytes; }
+    bytes = (bytes + 15) & ~(size_t)15;
+    if (ctx->flush_cap < bytes + 16) { cudaFree(ctx->flush); ctx->flush = nullptr; CK(cudaMalloc((void**)&ctx->flush, bytes + 16)); ctx->flush_cap = bytes + 16; }
     CK(cudaMemsetAsync(ctx->flush, 0x5a, bytes, ctx->stream));
+    k_read_sink<<<148 * 8, 256, 0, ctx->stream>>>((const uint4*)ctx->flush, bytes / 16, (unsigned*)(ctx->flush + bytes));
+    CK(cudaGetLastError());
     return TPOSE_OK;
 }
 
