@@ -290,7 +290,9 @@ def run_config5(args, pkg, synth, rank, world, local, dist, barrier, max_over_ra
     ratio = float(np.float32(w) / np.float32(h))
     total, cap = args.pairs, args.pair_level_cap
     sizes = (150, 500, 1500, 3000)
-    share = [g for g in range(total) if g % world == rank]          # global pair indices of this rank
+    shard = importlib.import_module("tpose_b200.shard")
+    lo, hi = shard.shard_range(total, world, rank)                    # contiguous block of pairs per rank
+    share = list(range(lo, hi))
     work = tempfile.mkdtemp(prefix=f"tpose_pairs_r{rank}_")
     pool = []                                                         # two distinct pairs, the same on every rank
     for k in range(2):
@@ -322,21 +324,11 @@ def run_config5(args, pkg, synth, rank, world, local, dist, barrier, max_over_ra
     packed = [ps.packed(i) for i in range(len(share))]
     t_compute = time.perf_counter() - t0
     length = len(packed[0]) if packed else 0
-    gather_ms, gathered = 0.0, None
-    if dist is not None:
-        import torch
-        mine = torch.from_numpy(np.stack(packed)).to(f"cuda:{local}")          # every pair has the same mesh sizes here
-        bucket = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.gather(mine, bucket, dst=0)
-        e1.record()
-        torch.cuda.synchronize()
-        gather_ms = e0.elapsed_time(e1)
-        if rank == 0:
-            gathered = [t.cpu().numpy() for t in bucket]
+    timing = {}
+    gathered = shard.gather_units({g: packed[i] for i, g in enumerate(share)}, total, dist, device=f"cuda:{local}" if dist is not None else "cpu",
+                                  timing=timing)
     t_total = max_over_ranks(time.perf_counter() - t0)
-    gather_ms = max_over_ranks(gather_ms)
+    gather_ms = max_over_ranks(timing.get("ms", 0.0))
     t_compute = max_over_ranks(t_compute)
     ps.close()
     out = None
@@ -347,8 +339,7 @@ def run_config5(args, pkg, synth, rank, world, local, dist, barrier, max_over_ra
         chk.run(tol=1e-6, level_cap=cap)
         again = chk.packed(0)
         chk.close()
-        owner, slot = g % world, [x for x in range(total) if x % world == (g % world)].index(g)
-        theirs = gathered[owner][slot] if gathered is not None else packed[slot]
+        theirs = gathered[g]
         identical = bool(np.array_equal(again.view(np.uint32), np.asarray(theirs, np.float32).view(np.uint32)))
         assert identical, "config 5: a pair recomputed on rank 0 differs from the gathered one"
         out = {"workload": f"{total} independent {w}x{h} view pairs (2 distinct synthetic pairs cycled), grid stacks {list(sizes)} triangles, warp level "
@@ -356,7 +347,8 @@ def run_config5(args, pkg, synth, rank, world, local, dist, barrier, max_over_ra
                            "triangulate(F,K,A,B), all pairs of a rank in shared launches, one process per GPU",
                "pairs_per_s": total / t_total, "seconds": t_total, "compute_seconds_max_rank": t_compute,
                "frames_per_pair": int(frames[0]), "levels_per_pair": int(levels[0]), "pairs_per_rank": len(share),
-               "gather": {"collective": "torch.distributed.gather over NCCL, inside the timed region" if dist is not None else "single rank: nothing to gather",
+               "gather": {"collective": "tpose_b200.shard.gather_units: torch.distributed.gather over NCCL (payload + lengths), inside the timed region"
+                                        if dist is not None else "single rank: nothing to gather",
                           "bytes_per_pair": int(4 * length), "bytes_total": int(4 * length * total), "ms": gather_ms},
                "recomputed_pair_identical": identical, "scaling": "strong"}
     shutil.rmtree(work, ignore_errors=True)

@@ -22,13 +22,16 @@ def owner_of(unit, n_units, world):
     raise IndexError(unit)
 
 
-def gather_units(local, n_units, dist=None, device="cpu", dst=0):
+def gather_units(local, n_units, dist=None, device="cpu", dst=0, timing=None):
     """local: {unit_index: float32 array (any shape, flattened on the wire)} for the units this rank
     owns.  Returns, on rank `dst`, {unit_index: flat float32 array} for ALL units; None elsewhere.
-    Ragged results are padded to the global maximum length (an all-reduce of one int), gathered
-    with ONE collective, and trimmed again."""
+    Ragged results are padded to the global maximum length (an all-reduce of one int) and gathered
+    with one collective for the payload and one for the int64 lengths, then trimmed again.
+    timing: optional dict; receives 'ms' (CUDA-event time of the two gathers when `device` is a GPU)."""
     import torch
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        if timing is not None:
+            timing["ms"] = 0.0
         return {u: np.asarray(a, np.float32).ravel() for u, a in local.items()}
     world, rank = dist.get_world_size(), dist.get_rank()
     lo, hi = shard_range(n_units, world, rank)
@@ -37,23 +40,38 @@ def gather_units(local, n_units, dist=None, device="cpu", dst=0):
     longest = torch.tensor([max([np.asarray(a).size for a in local.values()] + [0])], dtype=torch.int64, device=device)
     dist.all_reduce(longest, op=dist.ReduceOp.MAX)
     L = int(longest.item())
-    # row layout: [length, payload..., padding]
-    buf = torch.zeros((per_rank, L + 1), dtype=torch.float32, device=device)
+    host = np.zeros((per_rank, max(L, 1)), np.float32)
+    lens = np.zeros(per_rank, np.int64)
     for k, u in enumerate(range(lo, hi)):
-        a = torch.from_numpy(np.ascontiguousarray(np.asarray(local[u], np.float32).ravel()))
-        buf[k, 0] = float(a.numel())
-        buf[k, 1:1 + a.numel()] = a.to(device)
+        a = np.asarray(local[u], np.float32).ravel()
+        host[k, :a.size] = a
+        lens[k] = a.size
+    buf = torch.from_numpy(host).to(device)
+    nbuf = torch.from_numpy(lens).to(device)
     bucket = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    nbucket = [torch.empty_like(nbuf) for _ in range(world)] if rank == dst else None
+    on_gpu = str(device).startswith("cuda")
+    if on_gpu:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     dist.gather(buf, bucket, dst=dst)
+    dist.gather(nbuf, nbucket, dst=dst)
+    if on_gpu:
+        e1.record()
+        torch.cuda.synchronize()
+        if timing is not None:
+            timing["ms"] = float(e0.elapsed_time(e1))
+    elif timing is not None:
+        timing["ms"] = 0.0
     if rank != dst:
         return None
     out = {}
     for r in range(world):
         rlo, rhi = shard_range(n_units, world, r)
         rows = bucket[r].cpu().numpy()
+        ns = nbucket[r].cpu().numpy()
         for k, u in enumerate(range(rlo, rhi)):
-            n = int(rows[k, 0])
-            out[u] = rows[k, 1:1 + n].copy()
+            out[u] = rows[k, :int(ns[k])].copy()
     return out
 
 

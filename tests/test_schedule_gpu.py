@@ -69,6 +69,25 @@ def test_triangulate_schedule_frame_cap(dev, synth, tmp_path):
         assert ok, f"cap {cap}: {where}"
 
 
+def test_config2_schedule_prefix_at_1920x1080(dev, synth, tmp_path):
+    """configs[1] at its stated size: the topology schedule from the two-triangle mesh on the 1920x1080 synthetic
+    image, native raster -- the first 60 frames (converged frames with their flip sets and splits included) leave
+    the same mesh as the frame-by-frame reference loop.  (The whole schedule cannot be compared: with the
+    reference's step constant it does not get past a handful of triangles at this raster)"""
+    from oracle import schedule_oracle as S
+    w, h = 1920, 1080
+    img = synth.make_image(w, h, seed=1000)
+    ratio = float(np.float32(w) / np.float32(h))
+    fo, fr = str(tmp_path / "o.tri"), str(tmp_path / "r.tri")
+    cap = 60
+    ref = S.triangulate_loop(H.ref(), H.Tri, img, ratio, [1000], fr, cap)
+    got = _triangulate_ours(dev, img, ratio, [1000], fo, cap)
+    assert got["frames"] == ref["frames"] == cap
+    assert got["tr"]["counts"][0] > 2, "no split within the prefix: lengthen it"
+    ok, where = H.same_state(got["tr"], ref["tr"])
+    assert ok, where
+
+
 def test_warp_schedule_equals_frame_by_frame_reference(dev, synth, tmp_path):
     from oracle import schedule_oracle as S
     w, h = 192, 128
