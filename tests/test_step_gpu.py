@@ -41,6 +41,27 @@ def test_fused_step_triangulate_matches_oracle(cuda_pkg, synth, O, w, h, ntri, g
     ctx.close()
 
 
+def test_dense_mesh_on_a_small_raster(cuda_pkg, synth, O):
+    """10 000 triangles over 320x200 pixels: sub-pixel triangles, most instances cover no pixel centre at all, and
+    on the tile path every 64x64 tile is crossed by ~2 000 edges -- far beyond its work-list capacity, so the
+    tiles walk the edges in id-range chunks.  Still the oracle's bits."""
+    w, h = 320, 200
+    ratio = w / h
+    img = synth.make_image(w, h, seed=77)
+    pts, tri, _ = synth.mesh_for(10000, ratio)
+    ctx = cuda_pkg.Context(device=0, max_triangles=tri.shape[0], max_points=pts.shape[0])
+    ctx.set_image(0, img)
+    ctx.upload(pts, tri, ratio)
+    cur, gr = pts, None
+    for it in range(2):
+        ctx.step(0, cuda_pkg.TRIANGULATE, 1)
+        ref = O.step(img, cur, tri, ratio, O.TRIANGULATE, gr=gr)
+        _assert_step_equal(ctx.retrieve(), ref, ("cn", "ca", "ten"))
+        assert np.array_equal(ctx.retrieve_gradient(), ref["gr"])
+        cur, gr = ref["pts"], ref["gr"]
+    ctx.close()
+
+
 def test_fused_step_warp_matches_oracle(cuda_pkg, synth, O):
     w, h = 320, 180
     ratio = w / h
