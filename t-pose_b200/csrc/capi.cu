@@ -17,6 +17,7 @@
 #include <cstring>
 #include <algorithm>
 #include <cmath>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -1513,7 +1514,7 @@ struct MviewWs {
         (void)cudaGetLastError();
     }
 };
-thread_local std::vector<MviewWs*> g_mview_ws;
+thread_local std::vector<std::unique_ptr<MviewWs>> g_mview_ws;      // released when the thread ends
 
 int mview_fail(int code, const std::string& msg) { g_mview_error = msg; return code; }
 
@@ -1533,13 +1534,14 @@ int mview_workspace(int device, size_t bytes, MviewWs** out)
     }
     MCK(cudaSetDevice(device));
     MviewWs* ws = nullptr;
-    for (MviewWs* w : g_mview_ws) if (w->device == device) ws = w;
+    for (auto& w : g_mview_ws) if (w->device == device) ws = w.get();
     if (!ws) {
-        ws = new MviewWs();
-        ws->device = device;
-        MCK(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
-        MCK(cudaEventCreate(&ws->e0)); MCK(cudaEventCreate(&ws->e1));
-        g_mview_ws.push_back(ws);
+        auto fresh = std::make_unique<MviewWs>();      // (dropped again if any of its resources cannot be created)
+        fresh->device = device;
+        MCK(cudaStreamCreateWithFlags(&fresh->stream, cudaStreamNonBlocking));
+        MCK(cudaEventCreate(&fresh->e0)); MCK(cudaEventCreate(&fresh->e1));
+        g_mview_ws.push_back(std::move(fresh));
+        ws = g_mview_ws.back().get();
     }
     if (ws->cap < bytes) {
         MCK(cudaStreamSynchronize(ws->stream));
