@@ -537,7 +537,7 @@ static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int
         if (mid0) cudaEventRecord(mid0, st);
         k_tiles<kTileH><<<dim3(sh.grid_tiles, njobs), kTileThreads, tile_smem_bytes<kTileH>(), st>>>(jobs, flags);
         if (mid) cudaEventRecord(mid, st);
-        k_corners<<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame);
+        k_corners<EdgeRec><<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame);   // (k_tiles adds 64-bit words)
         return;
     }
     switch (sh.group) {
@@ -549,7 +549,8 @@ static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int
     default: launch_edges<32>(jobs, njobs, sh, set, flags, tol, frame, st); break;
     }
     if (mid) cudaEventRecord(mid, st);
-    k_corners<<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame);
+    if (sh.narrow) k_corners<EdgeRecNarrow><<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame);
+    else k_corners<EdgeRec><<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame);
 }
 static int launches_per_eval(const EvalShape& sh) { return sh.path == kPathTiles ? 3 : 2; }
 

@@ -56,6 +56,14 @@ struct __align__(16) EdgeRec {
     long long n, odd;
 };
 
+// The same record where 255*W*H < 2^31 (every image up to 3840x2160): no sum of the path leaves 32 bits except
+// the squared one, so k_corners adds half the words.  Used by k_edges<G, unsigned> -> k_corners<EdgeRecNarrow>.
+struct __align__(16) EdgeRecNarrow {
+    int r, g, b, n;
+    long long s2;
+    int odd, pad;
+};
+
 // Everything one image-step needs; lives in device memory so that a batch of independent jobs can
 // share one launch (blockIdx.y = job).
 struct EvalJob {
@@ -367,11 +375,18 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
             sr += shfl_xor_any(sr, o); sg += shfl_xor_any(sg, o); sb += shfl_xor_any(sb, o); s2 += shfl_xor_any(s2, o);
         }
         if (item < nitems && lane == 0) {
-            EdgeRec rec;
-            rec.r = sign * (long long)sr; rec.g = sign * (long long)sg; rec.b = sign * (long long)sb;
-            rec.s2 = sign * (long long)s2;
-            rec.n = sign * (long long)n; rec.odd = sign * (long long)odd;
-            J.rec[item] = rec;
+            if (sizeof(ACC) == 4) {          // narrow sums: 32-byte records
+                EdgeRecNarrow rec;
+                rec.r = sign * (int)sr; rec.g = sign * (int)sg; rec.b = sign * (int)sb; rec.n = sign * (int)n;
+                rec.s2 = sign * (long long)s2; rec.odd = sign * (int)odd; rec.pad = 0;
+                reinterpret_cast<EdgeRecNarrow*>(J.rec)[item] = rec;
+            } else {
+                EdgeRec rec;
+                rec.r = sign * (long long)sr; rec.g = sign * (long long)sg; rec.b = sign * (long long)sb;
+                rec.s2 = sign * (long long)s2;
+                rec.n = sign * (long long)n; rec.odd = sign * (long long)odd;
+                J.rec[item] = rec;
+            }
         }
     }
     TL(0, 5);
@@ -388,8 +403,17 @@ constexpr int kCornerThreads = 256;
 constexpr int kCornerWarps = kCornerThreads / 32;
 constexpr int kBaseBlocks = 16;          // blocks at the end of the grid that take the base variants
 
-__device__ __forceinline__ void add_rec(const EdgeRec* __restrict__ recs, int packed, int qlocal,
-                                        long long& sr, long long& sg, long long& sb, long long& s2, int& n, int& odd)
+// the three sums of a variant: 64-bit for the wide records, wrapping 32-bit for the narrow ones
+template <typename REC> struct SumOf { typedef long long type; };
+template <> struct SumOf<EdgeRecNarrow> { typedef int type; };
+
+template <typename REC, typename S>
+__device__ __forceinline__ void add_rec(const REC* __restrict__ recs, int packed, int qlocal,
+                                        S& sr, S& sg, S& sb, long long& s2, int& n, int& odd);
+
+template <>
+__device__ __forceinline__ void add_rec<EdgeRec, long long>(const EdgeRec* __restrict__ recs, int packed, int qlocal,
+                                                            long long& sr, long long& sg, long long& sb, long long& s2, int& n, int& odd)
 {
     // side runs second -> first: its first corner is the edge's second end point, and the sign flips
     const bool rev = packed < 0;
@@ -401,21 +425,52 @@ __device__ __forceinline__ void add_rec(const EdgeRec* __restrict__ recs, int pa
     else     { sr += v0.x; sg += v0.y; sb += v1.x; s2 += v1.y; n += (int)v2.x; odd += (int)v2.y; }
 }
 
+template <>
+__device__ __forceinline__ void add_rec<EdgeRecNarrow, int>(const EdgeRecNarrow* __restrict__ recs, int packed, int qlocal,
+                                                            int& sr, int& sg, int& sb, long long& s2, int& n, int& odd)
+{
+    const bool rev = packed < 0;
+    const int e = packed & 0x7fffffff;
+    const int q = (rev && qlocal) ? (qlocal <= 4 ? qlocal + 4 : qlocal - 4) : qlocal;
+    const int4* p = reinterpret_cast<const int4*>(recs + (size_t)e * kEdgeMoves + q);
+    const int4 v0 = __ldcg(p), v1 = __ldcg(p + 1);
+    const long long vs2 = (long long)(((unsigned long long)(unsigned)v1.y << 32) | (unsigned)v1.x);
+    if (rev) { sr -= v0.x; sg -= v0.y; sb -= v0.z; n -= v0.w; s2 -= vs2; odd -= v1.z; }
+    else     { sr += v0.x; sg += v0.y; sb += v0.z; n += v0.w; s2 += vs2; odd += v1.z; }
+}
+
+// floor(a / n) for three non-negative 32-bit numerators and one divisor 1 <= n < 2^31 with a single hardware
+// division: M = ceil(2^32 / n), q' = mulhi(a, M) is the quotient or one more (a * (M n - 2^32) < 2^32 n), fixed by
+// one multiply-compare.  The reference divides ivec3 by int (triangle.fs:40).
+__device__ __forceinline__ void div3_nonneg(unsigned a0, unsigned a1, unsigned a2, unsigned n, int& q0, int& q1, int& q2)
+{
+    if (n == 1u) { q0 = (int)a0; q1 = (int)a1; q2 = (int)a2; return; }
+    const unsigned M = 0xFFFFFFFFu / n + 1u;                 // ceil(2^32 / n) for n >= 2 (2^32 itself is never a multiple's successor here)
+    unsigned t0 = __umulhi(a0, M), t1 = __umulhi(a1, M), t2 = __umulhi(a2, M);
+    if ((unsigned long long)t0 * n > a0) --t0;
+    if ((unsigned long long)t1 * n > a1) --t1;
+    if ((unsigned long long)t2 * n > a2) --t2;
+    q0 = (int)t0; q1 = (int)t1; q2 = (int)t2;
+}
+
 // variant k of triangle t: three edge records -> moments -> cn / ca / ten as the flags ask.
 // Returns the (wrapped int32) energy.
+template <typename REC>
 __device__ __forceinline__ int eval_variant(const EvalJob& J, unsigned flags, int* __restrict__ cn, int4* __restrict__ ca,
                                             int* __restrict__ ten, int t, int k)
 {
+    typedef typename SumOf<REC>::type S;
+    const REC* recs = reinterpret_cast<const REC*>(J.rec);
     const int4 te = __ldg(J.tri_edges + t);
     // side j has its first corner moved, side j+2 its second one; the third side is as it is
     const int j = (k - 1) >> 2, s = (k - 1) & 3, j2 = (j >= 1) ? j - 1 : 2;
     const int q0 = (k == 0) ? 0 : (j == 0 ? 1 + s : (j2 == 0 ? 5 + s : 0));
     const int q1 = (k == 0) ? 0 : (j == 1 ? 1 + s : (j2 == 1 ? 5 + s : 0));
     const int q2 = (k == 0) ? 0 : (j == 2 ? 1 + s : (j2 == 2 ? 5 + s : 0));
-    long long sr = 0, sg = 0, sb = 0, s2 = 0; int n = 0, odd = 0;
-    add_rec(J.rec, te.x, q0, sr, sg, sb, s2, n, odd);
-    add_rec(J.rec, te.y, q1, sr, sg, sb, s2, n, odd);
-    add_rec(J.rec, te.z, q2, sr, sg, sb, s2, n, odd);
+    S sr = 0, sg = 0, sb = 0; long long s2 = 0; int n = 0, odd = 0;
+    add_rec<REC, S>(recs, te.x, q0, sr, sg, sb, s2, n, odd);
+    add_rec<REC, S>(recs, te.y, q1, sr, sg, sb, s2, n, odd);
+    add_rec<REC, S>(recs, te.z, q2, sr, sg, sb, s2, n, odd);
     if (n < 0) { n = -n; odd = -odd; sr = -sr; sg = -sg; sb = -sb; s2 = -s2; }
     const int g = k * J.NT + t;
     if (flags & EV_WRITE_CN) cn[g] = n;
@@ -433,17 +488,20 @@ __device__ __forceinline__ int eval_variant(const EvalJob& J, unsigned flags, in
             // |sums| <= 255*n < 2^31 here, so the quotient is a 32-bit one unless an accumulator
             // would have wrapped -- then take the general path
             if (n > 0) {
-                if (sr == (int)sr && sg == (int)sg && sb == (int)sb) { m0 = (int)sr / n; m1 = (int)sg / n; m2 = (int)sb / n; }
-                else { m0 = (int)(sr / n); m1 = (int)(sg / n); m2 = (int)(sb / n); }
+                if (sizeof(S) == 4 || (sr == (int)sr && sg == (int)sg && sb == (int)sb)) {
+                    if ((int)sr >= 0 && (int)sg >= 0 && (int)sb >= 0) div3_nonneg((unsigned)(int)sr, (unsigned)(int)sg, (unsigned)(int)sb, (unsigned)n, m0, m1, m2);
+                    else { m0 = (int)sr / n; m1 = (int)sg / n; m2 = (int)sb / n; }
+                } else { m0 = (int)((long long)sr / n); m1 = (int)((long long)sg / n); m2 = (int)((long long)sb / n); }
             } else have = false;
         }
-        const long long e = have ? energy_closed_form(n, odd, sr, sg, sb, s2, m0, m1, m2) : 0ll;
+        const long long e = have ? energy_closed_form(n, odd, (long long)sr, (long long)sg, (long long)sb, s2, m0, m1, m2) : 0ll;
         e32 = (int)(unsigned)(unsigned long long)e;   // int32 accumulator wraps
         ten[g] = e32;
     }
     return e32;
 }
 
+template <typename REC>
 __global__ void __launch_bounds__(kCornerThreads)
 k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame)
 {
@@ -466,7 +524,7 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame)
         // base variants, one thread each
         const bool hist = (flags & EV_HISTORY) && frame >= 0 && !(flags & EV_FINAL);
         for (int t = ((int)blockIdx.x - nvb) * kCornerThreads + tid; t < J.NT; t += kBaseBlocks * kCornerThreads) {
-            const int e = eval_variant(J, flags, cn, ca, ten, t, 0);
+            const int e = eval_variant<REC>(J, flags, cn, ca, ten, t, 0);
             if (hist) J.hist_ten[(size_t)frame * J.NT + t] = e;       // harmless if this frame turns out to be discarded
         }
         TL(1, 2);
@@ -502,7 +560,7 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame)
             if (c < c1) {
                 const int packed = __ldg(J.corners + c);          // triangle << 2 | corner
                 const int t = packed >> 2, j = packed & 3;
-                const unsigned e = (unsigned)eval_variant(J, flags, cn, ca, ten, t, 1 + 4 * j + s);
+                const unsigned e = (unsigned)eval_variant<REC>(J, flags, cn, ca, ten, t, 1 + 4 * j + s);
                 // gradient.cs:27-34: x from the +-dp moves in x (s = 0, 1), y from s = 2, 3
                 const unsigned signed_e = (s & 1) ? 0u - e : e;
                 if (s < 2) gx += signed_e; else gy += signed_e;
