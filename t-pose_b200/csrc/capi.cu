@@ -26,7 +26,7 @@ using namespace tpose_dev;
 // Launch geometry of one evaluation.  Grid sizes are quantised (power of two, at most one full
 // wave) and the kernels stride, so a captured sequence stays valid while the mesh grows.
 // path: 0 = row-prefix table gathers (k_edges), 1 = TMA-staged tiles (k_setup + k_tiles)
-struct EvalShape { int group, grid_e, grid_t; bool narrow; int path, grid_s, grid_tiles; };
+struct EvalShape { int group, grid_e, grid_t; bool narrow; int path, grid_s, grid_tiles; int grid_b; };
 constexpr int kPathTable = 0, kPathTiles = 1;
 constexpr int kTileH = 64;
 // a sequence of evaluations (see issue_sequence) and its instantiated graph
@@ -497,20 +497,25 @@ static int pick_group(const tpose_cuda_ctx* ctx, int NT, int H)
 // 32-bit colour sums are exact while 255*W*H < 2^31
 static bool narrow_sums(int W, int H) { return 255ll * W * H < (1ll << 31); }
 
-constexpr int kMaxGridBlocks = 148 * 4;
+constexpr int kSMs = 148;
+constexpr int kMaxGridBlocks = kSMs * 4;
 
-static int quantised_grid(long long blocks_needed)
+static int quantised_grid(long long blocks_needed, int cap = kMaxGridBlocks)
 {
     int g = 32;
-    while (g < blocks_needed && g < kMaxGridBlocks) g <<= 1;
-    return g < kMaxGridBlocks ? g : kMaxGridBlocks;
+    while (g < blocks_needed && g < cap) g <<= 1;
+    return g < cap ? g : cap;
 }
 
-static EvalShape make_shape(int group, int max_np, int max_ne, bool narrow, int path, int max_tiles)
+static EvalShape make_shape(int group, int max_np, int max_ne, int max_nt, bool narrow, int path, int max_tiles)
 {
     const int per_block = kEdgeThreads / group;
+    // k_corners: blocks for the base variants in proportion to NT (one variant per thread), and vertex blocks up to
+    // what is resident together with them, so that neither part of the grid takes a second turn on a busy SM
+    const int base_blocks = quantised_grid((max_nt + kCornerThreads - 1) / kCornerThreads, 128) < 16 ? 16
+                            : quantised_grid((max_nt + kCornerThreads - 1) / kCornerThreads, 128);
     EvalShape sh{group, quantised_grid(((long long)max_ne * kEdgeMoves + per_block - 1) / per_block),
-                 quantised_grid((max_np + kCornerWarps - 1) / kCornerWarps), narrow, path, 0, 0};
+                 quantised_grid((max_np + kCornerWarps - 1) / kCornerWarps, kSMs * kCornerBlocksPerSM - base_blocks), narrow, path, 0, 0, base_blocks};
     if (path == kPathTiles) {
         // (group, grid_e and narrow do not exist on the tile path: keep them out of the graph key)
         sh.group = 1; sh.grid_e = 0; sh.narrow = true;
@@ -537,7 +542,7 @@ static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int
         if (mid0) cudaEventRecord(mid0, st);
         k_tiles<kTileH><<<dim3(sh.grid_tiles, njobs), kTileThreads, tile_smem_bytes<kTileH>(), st>>>(jobs, flags);
         if (mid) cudaEventRecord(mid, st);
-        k_corners<EdgeRec><<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame);   // (k_tiles adds 64-bit words)
+        k_corners<EdgeRec><<<dim3(sh.grid_t + sh.grid_b, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame, sh.grid_b);   // (k_tiles adds 64-bit words)
         return;
     }
     switch (sh.group) {
@@ -549,8 +554,8 @@ static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int
     default: launch_edges<32>(jobs, njobs, sh, set, flags, tol, frame, st); break;
     }
     if (mid) cudaEventRecord(mid, st);
-    if (sh.narrow) k_corners<EdgeRecNarrow><<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame);
-    else k_corners<EdgeRec><<<dim3(sh.grid_t + kBaseBlocks, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame);
+    if (sh.narrow) k_corners<EdgeRecNarrow><<<dim3(sh.grid_t + sh.grid_b, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame, sh.grid_b);
+    else k_corners<EdgeRec><<<dim3(sh.grid_t + sh.grid_b, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame, sh.grid_b);
 }
 static int launches_per_eval(const EvalShape& sh) { return sh.path == kPathTiles ? 3 : 2; }
 
@@ -581,7 +586,7 @@ static bool same_key(const SeqKey& a, const SeqKey& b)
     return a.jobs == b.jobs && a.njobs == b.njobs && a.kind == b.kind && a.len == b.len && a.first_set == b.first_set &&
            a.flags == b.flags && a.tol == b.tol && a.shape.group == b.shape.group && a.shape.grid_e == b.shape.grid_e &&
            a.shape.grid_t == b.shape.grid_t && a.shape.narrow == b.shape.narrow && a.shape.path == b.shape.path &&
-           a.shape.grid_s == b.shape.grid_s && a.shape.grid_tiles == b.shape.grid_tiles;
+           a.shape.grid_s == b.shape.grid_s && a.shape.grid_tiles == b.shape.grid_tiles && a.shape.grid_b == b.shape.grid_b;
 }
 
 static int issue_sequence(tpose_cuda_ctx* ctx, const SeqKey& key)
@@ -691,7 +696,7 @@ static int sync_job(tpose_cuda_ctx* ctx, int slot, int flavour)
 static EvalShape shape_of(const tpose_cuda_ctx* ctx, int slot)
 {
     const ImageSlot& im = ctx->img[slot];
-    return make_shape(pick_group(ctx, ctx->NT, im.H), ctx->NP, ctx->NE, narrow_sums(im.W, im.H), ctx->path, im.ntx * im.nty);
+    return make_shape(pick_group(ctx, ctx->NT, im.H), ctx->NP, ctx->NE, ctx->NT, narrow_sums(im.W, im.H), ctx->path, im.ntx * im.nty);
 }
 
 static int eval(tpose_cuda_ctx* ctx, int slot, int flavour, int set, unsigned flags, double tol = 0.0)
@@ -835,7 +840,7 @@ static int frame_mapped(tpose_cuda_ctx* ctx, int slot, int flavour, const float*
         if (c.in == d_in && c.ten == d_ten && c.cn == d_cn && c.ca == d_ca && c.out == d_out && c.set == set && c.nt == ctx->NT && c.np == ctx->NP &&
             c.slot == slot && c.flavour == flavour && c.job == ctx->job_dev && c.shape.group == sh.group && c.shape.grid_e == sh.grid_e &&
             c.shape.grid_t == sh.grid_t && c.shape.narrow == sh.narrow && c.shape.path == sh.path && c.shape.grid_s == sh.grid_s &&
-            c.shape.grid_tiles == sh.grid_tiles) g = &c;
+            c.shape.grid_tiles == sh.grid_tiles && c.shape.grid_b == sh.grid_b) g = &c;
     if (!g) {
         cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
         cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
@@ -1077,7 +1082,7 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
     tpose_cuda_ctx* lead = ctxs[0];
     tpose_cuda_ctx* ctx = lead;   // for CK
     std::vector<EvalJob> jobs((size_t)n);
-    int mxp = 0, mxe = 0, mxt = 0; double rows = 0.0, items = 0.0; bool narrow = true;
+    int mxp = 0, mxe = 0, mxt = 0, mxn = 0; double rows = 0.0, items = 0.0; bool narrow = true;
     for (int i = 0; i < n; i++) {
         const int slot = slots ? slots[i] : 0;
         int rc = check_ready(ctxs[i], slot, flavour);
@@ -1093,6 +1098,7 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
         jobs[(size_t)i].flip = ctxs[i]->cur ^ lead->cur;   // contexts need not have done the same number of steps
         mxp = ctxs[i]->NP > mxp ? ctxs[i]->NP : mxp;
         mxe = ctxs[i]->NE > mxe ? ctxs[i]->NE : mxe;
+        mxn = std::max(mxn, ctxs[i]->NT);
         mxt = std::max(mxt, ctxs[i]->img[slot].ntx * ctxs[i]->img[slot].nty);
         items += (double)ctxs[i]->NE * kEdgeMoves;
         narrow = narrow && narrow_sums(ctxs[i]->img[slot].W, ctxs[i]->img[slot].H);
@@ -1105,7 +1111,7 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
     }
     CK(cudaMemcpyAsync(lead->batch_jobs, jobs.data(), sizeof(EvalJob) * n, cudaMemcpyHostToDevice, lead->stream));
     CK(cudaStreamSynchronize(lead->stream));   // `jobs` is a local
-    *shape = make_shape(valid_group(lead->group) ? lead->group : group_for(rows / n, items), mxp, mxe, narrow, lead->path, mxt);
+    *shape = make_shape(valid_group(lead->group) ? lead->group : group_for(rows / n, items), mxp, mxe, mxn, narrow, lead->path, mxt);
     return TPOSE_OK;
 }
 

@@ -401,7 +401,7 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
 
 constexpr int kCornerThreads = 256;
 constexpr int kCornerWarps = kCornerThreads / 32;
-constexpr int kBaseBlocks = 16;          // blocks at the end of the grid that take the base variants
+constexpr int kCornerBlocksPerSM = 5;    // 48 registers x 256 threads (the wide-record variant holds 4)
 
 // the three sums of a variant: 64-bit for the wide records, wrapping 32-bit for the narrow ones
 template <typename REC> struct SumOf { typedef long long type; };
@@ -503,7 +503,7 @@ __device__ __forceinline__ int eval_variant(const EvalJob& J, unsigned flags, in
 
 template <typename REC>
 __global__ void __launch_bounds__(kCornerThreads)
-k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame)
+k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame, int base_blocks)
 {
     __shared__ EvalJob J;
     const int tid = threadIdx.x;
@@ -518,12 +518,12 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame)
     set ^= J.flip;
     int* const cn = J.cn[set]; int4* const ca = J.ca[set]; int* const ten = J.ten[set];
 
-    const int nvb = (int)gridDim.x - kBaseBlocks;           // blocks that take vertices
+    const int nvb = (int)gridDim.x - base_blocks;           // blocks that take vertices; the last base_blocks take the base variants
     if ((flags & EV_FINAL) && blockIdx.x != 0) return;      // check-only evaluation: block 0 records the verdict
     if ((int)blockIdx.x >= nvb) {
         // base variants, one thread each
         const bool hist = (flags & EV_HISTORY) && frame >= 0 && !(flags & EV_FINAL);
-        for (int t = ((int)blockIdx.x - nvb) * kCornerThreads + tid; t < J.NT; t += kBaseBlocks * kCornerThreads) {
+        for (int t = ((int)blockIdx.x - nvb) * kCornerThreads + tid; t < J.NT; t += base_blocks * kCornerThreads) {
             const int e = eval_variant<REC>(J, flags, cn, ca, ten, t, 0);
             if (hist) J.hist_ten[(size_t)frame * J.NT + t] = e;       // harmless if this frame turns out to be discarded
         }
