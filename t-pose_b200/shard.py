@@ -28,11 +28,11 @@ def gather_units(local, n_units, dist=None, device="cpu", dst=0, timing=None):
     Ragged results are padded to the global maximum length (an all-reduce of one int) and gathered
     with one collective for the payload and one for the int64 lengths, then trimmed again.
     timing: optional dict; receives 'ms' (CUDA-event time of the two gathers when `device` is a GPU)."""
-    import torch
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         if timing is not None:
             timing["ms"] = 0.0
         return {u: np.asarray(a, np.float32).ravel() for u, a in local.items()}
+    import torch          # (only with a process group: a single rank never pays the import)
     world, rank = dist.get_world_size(), dist.get_rank()
     lo, hi = shard_range(n_units, world, rank)
     assert sorted(local) == list(range(lo, hi)), "rank does not hold exactly its shard"
