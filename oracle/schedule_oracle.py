@@ -64,7 +64,7 @@ def _flip_set(terr, halfedges, ntri):
     return dict(sorted(hflip.items()))
 
 
-def triangulate_loop(R, Tri, img, ratio, exportlist, trifile, max_frames, tol=1e-4, trace=None):
+def triangulate_loop(R, Tri, img, ratio, exportlist, trifile, max_frames, tol=1e-4, trace=None, updates=None):
     """R: the reference library (hostlib.ref()); Tri: hostlib.Tri.  exportlist is popped from the
     back like main.cpp:19-31.  Returns dict(frames, tr (final Tri.get()), finished)."""
     import ctypes as C
@@ -162,7 +162,9 @@ def triangulate_loop(R, Tri, img, ratio, exportlist, trifile, max_frames, tol=1e
                 updated = True
             ta += 1
         if updated:                                             # main.cpp:348-351
-            tr.gettoterr()
+            tot = tr.gettoterr()
+            if updates is not None:
+                updates.append((tr.counts()[0], float(tot), frames))   # what the program prints: "NT toterr"
             upload()
         computecolors()                                         # the pipeline, main.cpp:180-184
     out = dict(frames=frames, tr=tr.get(), finished=finished)

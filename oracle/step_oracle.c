@@ -61,6 +61,7 @@ void tpo_set_dp_law(int which) { g_dp_law = which; }
 float tpo_dp(int NT, int flavour)
 {
     float dp = 0.05f;
+    if (g_dp_law == 2) return dp;            /* no cooling at all: the oldest traces of the reference's test program */
     if (g_dp_law >= 0) flavour = g_dp_law;
     if (flavour == TPO_WARP) dp = dp / (1.0f + 9.0f * (float)NT / 1000.0f);
     else                     dp = dp / (1.0f + 4.0f * (float)NT / 3000.0f);
