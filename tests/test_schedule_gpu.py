@@ -147,6 +147,15 @@ def test_ported_programs_write_the_same_files_as_the_library_calls(dev, synth, t
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "levels" in out.stdout, out.stdout + out.stderr
     assert os.path.getsize(paths[0] + ".tri.warp") == os.path.getsize(paths[0] + ".tri")
+    # the same program on the tile-streaming kernels (no row-prefix table there, so converged frames take the
+    # reference's two full re-evaluations instead of tpose_cuda_eval_list): same file
+    tiles_in = str(tmp_path / "tiles.ppm")
+    import shutil
+    shutil.copy(paths[0], tiles_in)
+    out = subprocess.run([exe_t, "-i", tiles_in, "-native", "-frames", "3000"], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, TPOSE_CUDA_PATH="tiles"))
+    assert out.returncode == 0 and "steps/s" in out.stdout, out.stdout + out.stderr
+    assert open(tiles_in + ".tri", "rb").read() == open(paths[0] + ".tri", "rb").read()
     # extension -t: continue from the finest level of an existing stack.  io::read leaves `colors` at that
     # level's NT; every level exported afterwards must still carry mean colours (bytes), not raw sums.
     import shutil, struct
