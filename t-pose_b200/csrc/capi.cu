@@ -16,8 +16,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
-#include <atomic>
-#include <chrono>
 #include <cmath>
 #include <memory>
 #include <string>
@@ -105,8 +103,6 @@ struct tpose_cuda_ctx {
     int group = 0;                    // lanes per edge (0 = pick from NT and H)
     std::vector<SeqGraph> graphs; uint64_t graph_clock = 0; bool use_graphs = true;
     std::vector<FrameGraph> frame_graphs;      // tpose_cuda_frame with pinned caller buffers
-    unsigned* frame_sync = nullptr;                   // device: [0] finished blocks of k_frame_out, [1] frames completed
-    volatile unsigned* h_frame_seq = nullptr; unsigned* h_frame_seq_dev = nullptr; unsigned frame_seq_host = 0;   // mapped completion word
     const void* frame_host[5] = {(const void*)1, nullptr, nullptr, nullptr, nullptr}; void* frame_alias[5] = {};   // last pointer set seen and its device aliases
     bool mid_valid = false, time_kernels = false;
     // read-back cache filled by tpose_cuda_run in the same synchronisation as its verdict: the points and
@@ -220,19 +216,7 @@ extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, 
     ALLOC(ctx->gbox, sizeof(unsigned) * ((3 * (size_t)max_triangles + kEdgeGroup - 1) / kEdgeGroup + 1));
     ALLOC(ctx->ticket, sizeof(unsigned) * 2);
     ALLOC(ctx->job_dev, sizeof(EvalJob));
-    ALLOC(ctx->frame_sync, sizeof(unsigned) * 2);
 #undef ALLOC
-    cudaMemsetAsync(ctx->frame_sync, 0, sizeof(unsigned) * 2, ctx->stream);
-    {   // completion word of tpose_cuda_frame's mapped path (optional: without it the frame drains the stream)
-        void* hp = nullptr; void* dp = nullptr;
-        if (cudaHostAlloc(&hp, 64, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
-            *(unsigned*)hp = 0u;
-            ctx->h_frame_seq = (volatile unsigned*)hp; ctx->h_frame_seq_dev = (unsigned*)dp;
-        } else {
-            if (hp) cudaFreeHost(hp);
-            (void)cudaGetLastError();
-        }
-    }
     for (int s = 0; s < 2; s++) {
         cudaMemsetAsync(ctx->cn[s], 0, sizeof(int) * nv, ctx->stream);
         cudaMemsetAsync(ctx->ca[s], 0, sizeof(int4) * nv, ctx->stream);
@@ -287,8 +271,7 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
     cudaFree(ctx->edges); cudaFree(ctx->tri_edges); cudaFree(ctx->corner_off); cudaFree(ctx->corners); cudaFree(ctx->rec);
     cudaFree(ctx->gr); cudaFree(ctx->wbuf); cudaFree(ctx->ticket);
     cudaFree(ctx->report); cudaFree(ctx->ids); cudaFree(ctx->flush); cudaFree(ctx->list_buf);
-    cudaFree(ctx->job_dev); cudaFree(ctx->batch_jobs); cudaFree(ctx->frame_sync);
-    if (ctx->h_frame_seq) cudaFreeHost((void*)ctx->h_frame_seq);
+    cudaFree(ctx->job_dev); cudaFree(ctx->batch_jobs);
     if (ctx->h_report) cudaFreeHost(ctx->h_report);
     cudaFree(ctx->d_hist_pts); cudaFree(ctx->d_hist_ten); cudaFree(ctx->d_hist_err); cudaFree(ctx->d_hist_mask); cudaFree(ctx->d_hist_gr);
     if (ctx->h_hist_pts) cudaFreeHost(ctx->h_hist_pts);
@@ -803,12 +786,7 @@ __global__ void k_frame_in(const float2* __restrict__ host_pts, float2* __restri
     if (i < np) pts[i] = host_pts[i];
 }
 
-struct FrameOut {
-    const int* ten; const int* cn; const int4* ca; const float2* pts; int* h_ten; int* h_cn; int4* h_ca; float2* h_pts; int nv, np;
-    unsigned* done_blocks;           // device: blocks of this launch that have finished their stores
-    unsigned* seq;                   // device: frames completed so far
-    volatile unsigned* h_seq;        // mapped host word: the last block publishes the new frame count here
-};
+struct FrameOut { const int* ten; const int* cn; const int4* ca; const float2* pts; int* h_ten; int* h_cn; int4* h_ca; float2* h_pts; int nv, np; };
 
 __device__ __forceinline__ void copy_words(const int* __restrict__ src, int* __restrict__ dst, int n, int tid, int nthreads)
 {
@@ -826,20 +804,6 @@ __global__ void __launch_bounds__(256) k_frame_out(FrameOut f)
     if (f.h_cn) copy_words(f.cn, f.h_cn, f.nv, tid, nthreads);
     if (f.h_ca) copy_words(reinterpret_cast<const int*>(f.ca), reinterpret_cast<int*>(f.h_ca), 4 * f.nv, tid, nthreads);
     if (f.h_pts) copy_words(reinterpret_cast<const int*>(f.pts), reinterpret_cast<int*>(f.h_pts), 2 * f.np, tid, nthreads);
-    // completion word: every block makes its stores visible system-wide and counts itself; the last one publishes
-    // the frame number in host memory, where the caller spins on it instead of waiting for the stream to drain
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned prev = atomicAdd(f.done_blocks, 1u);
-        if (prev == gridDim.x - 1) {
-            *f.done_blocks = 0u;
-            const unsigned s = *f.seq + 1u;
-            *f.seq = s;
-            __threadfence_system();
-            if (f.h_seq) *f.h_seq = s;
-        }
-    }
 }
 
 // the device-side alias of a host pointer if the memory is page-locked and mapped, else nullptr
@@ -883,8 +847,7 @@ static int frame_mapped(tpose_cuda_ctx* ctx, int slot, int flavour, const float*
         if (e == cudaSuccess) {
             if (d_in) k_frame_in<<<(ctx->NP + 255) / 256, 256, 0, ctx->stream>>>((const float2*)d_in, ctx->pts, ctx->NP);
             launch_eval(sh, ctx->job_dev, 1, set, fused_flags(flavour), 0.0, -1, ctx->stream);
-            FrameOut f{ctx->ten[set], ctx->cn[set], ctx->ca[set], ctx->pts, (int*)d_ten, (int*)d_cn, (int4*)d_ca, (float2*)d_out, kVariants * ctx->NT, ctx->NP,
-                       ctx->frame_sync, ctx->frame_sync + 1, ctx->h_frame_seq_dev};
+            FrameOut f{ctx->ten[set], ctx->cn[set], ctx->ca[set], ctx->pts, (int*)d_ten, (int*)d_cn, (int4*)d_ca, (float2*)d_out, kVariants * ctx->NT, ctx->NP};
             k_frame_out<<<64, 256, 0, ctx->stream>>>(f);
             e = cudaStreamEndCapture(ctx->stream, &graph);
         }
@@ -899,21 +862,7 @@ static int frame_mapped(tpose_cuda_ctx* ctx, int slot, int flavour, const float*
     CK(cudaGraphLaunch(g->exec, ctx->stream));
     ctx->launches += launches_per_eval(sh) + (d_in ? 2 : 1);
     ctx->cur = set;
-    // wait for the completion word (a few hundred polls of one cache line); a frame that does not report within
-    // 20 ms -- or a context without the word -- falls back to draining the stream, which also surfaces errors
-    const unsigned want = ++ctx->frame_seq_host;
-    bool seen = false;
-    if (ctx->h_frame_seq) {
-        const auto t0 = std::chrono::steady_clock::now();
-        for (unsigned spins = 0; !seen; spins++) {
-            if (*ctx->h_frame_seq == want) { seen = true; std::atomic_thread_fence(std::memory_order_acquire); break; }
-            if ((spins & 1023u) == 1023u && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(20)) break;
-        }
-    }
-    if (!seen) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (ctx->h_frame_seq && *ctx->h_frame_seq != want) return fail(ctx, TPOSE_ERR_CUDA, "frame: the device did not report completion");
-    }
+    CK(cudaStreamSynchronize(ctx->stream));
     *done = true;
     return TPOSE_OK;
 }
