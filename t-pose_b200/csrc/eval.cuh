@@ -268,38 +268,62 @@ template <typename T> __device__ __forceinline__ T shfl_xor_any(T v, int o) { re
 // Walks the rows of one edge (this lane's share: rows r, r+G, ...) and sums the table entries at
 // the crossings.  ACC is the accumulator type of the three colour sums: 32 bits are enough when
 // 255*W*H < 2^31 (every image up to 3840x2160), else 64.
-// Rows are taken kWalkBatch at a time: all loads of a batch are issued (predicated off past the
-// end of the edge) before the first one is consumed, so a lane pays one memory latency per batch,
-// not per row, and there is no serial remainder loop.
+// Rows are taken kWalkBatch at a time: all loads of a batch are issued before the first one is
+// consumed, so a lane pays one memory latency per batch, not per row; whole batches first, then
+// one tail batch whose slots past the end of the edge read a zero entry.
 #ifndef TPOSE_WALK_BATCH
 #define TPOSE_WALK_BATCH 8
 #endif
 constexpr int kWalkBatch = TPOSE_WALK_BATCH;
+
+// A table entry through the read-only path with the L2 fetch size pinned to 64 bytes (SASS: LDG.E.LTC64B.128.CONSTANT).
+// A plain load that misses L2 makes it fetch the whole 128-byte line from DRAM (measured on B200 with a strided
+// probe: 128 B of dram__bytes_read per 16-byte load at any stride >= 128, every load flavour; 64 B with this
+// qualifier or with a bulk copy; cudaLimitMaxL2FetchGranularity changes nothing).  The walk is a gather -- the next
+// row's crossing is in another line -- so the second half of the line is bytes nobody asked for.
+__device__ __forceinline__ uint4 ldg_entry(const uint4* p)
+{
+    uint4 v;
+    asm("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// one batch of kWalkBatch rows.  TAIL: the edge may end inside the batch -- a slot past its end reads entry 0
+// (column 0 of row 0: an all-zero prefix), an unconditional load of zeros instead of a predicated load into
+// zeroed registers; full batches carry no per-slot test at all.
+template <int G, typename ACC, typename REM, bool TAIL>
+__device__ __forceinline__ void walk_batch(const int rr, const int r_end, int& q, const int dq, REM& rem, const REM den, const REM dr,
+                                           const uint4* __restrict__ table, int& row, const int rstep, const int W,
+                                           unsigned& n, unsigned& odd, ACC& sr, ACC& sg, ACC& sb, unsigned long long& s2)
+{
+    uint4 e[kWalkBatch];
+    int c[kWalkBatch];
+#pragma unroll
+    for (int u = 0; u < kWalkBatch; u++) {
+        const bool on = !TAIL || rr + u * G < r_end;
+        const int cc = min(max(q, 0), W);
+        c[u] = on ? cc : 0;
+        e[u] = ldg_entry(table + (on ? row + cc : 0));      // entry index: (W+1)*H <= 4096*8192 fits 32 bits
+        q += dq; rem += dr;
+        if (rem >= den) { rem -= den; ++q; }
+        row += rstep;
+    }
+#pragma unroll
+    for (int u = 0; u < kWalkBatch; u++) {
+        n += (unsigned)c[u]; odd += e[u].x >> 20; sr += (ACC)(e[u].x & 0xFFFFFu);
+        sg += (ACC)e[u].y; sb += (ACC)e[u].z; s2 += e[u].w;
+    }
+}
 
 template <int G, typename ACC, typename REM>
 __device__ __forceinline__ void walk_rows(int rr, const int r_end, int q, const int dq, REM rem, const REM den, const REM dr,
                                           const uint4* __restrict__ table, int row, const int rstep, const int W,
                                           unsigned& n, unsigned& odd, ACC& sr, ACC& sg, ACC& sb, unsigned long long& s2)
 {
-    for (; rr < r_end; rr += kWalkBatch * G) {
-        uint4 e[kWalkBatch];
-        int c[kWalkBatch];
-#pragma unroll
-        for (int u = 0; u < kWalkBatch; u++) {
-            const bool on = rr + u * G < r_end;
-            c[u] = on ? min(max(q, 0), W) : 0;
-            e[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (on) e[u] = __ldg(table + (row + c[u]));     // entry index: (W+1)*H <= 4096*8192 fits 32 bits
-            q += dq; rem += dr;
-            if (rem >= den) { rem -= den; ++q; }
-            row += rstep;
-        }
-#pragma unroll
-        for (int u = 0; u < kWalkBatch; u++) {
-            n += (unsigned)c[u]; odd += e[u].x >> 20; sr += (ACC)(e[u].x & 0xFFFFFu);
-            sg += (ACC)e[u].y; sb += (ACC)e[u].z; s2 += e[u].w;
-        }
-    }
+    for (; rr + (kWalkBatch - 1) * G < r_end; rr += kWalkBatch * G)
+        walk_batch<G, ACC, REM, false>(rr, r_end, q, dq, rem, den, dr, table, row, rstep, W, n, odd, sr, sg, sb, s2);
+    if (rr < r_end)
+        walk_batch<G, ACC, REM, true>(rr, r_end, q, dq, rem, den, dr, table, row, rstep, W, n, odd, sr, sg, sb, s2);
 }
 
 template <int G, typename ACC>
