@@ -65,6 +65,8 @@ int main(int argc, char* args[])
               << ", flips " << rep.flips << ", prunes " << rep.prunes << ", collapses " << rep.collapses << ", idle host frames "
               << rep.idle_host_frames << ", exports " << rep.exports << ", " << tr.NT << " triangles, " << sec << " s ("
               << rep.s_device << " in tpose_cuda_run, " << rep.s_host << " in the host body), " << rep.frames / sec << " steps/s" << std::endl;
+    std::cout << "runs " << rep.runs << ": " << rep.frames_asked << " frames asked, " << rep.frames_run << " run, " << rep.frames << " kept; "
+              << rep.resyncs << " runs cut short by a host edit; device-timed " << rep.ms_device_events / 1000.0 << " s" << std::endl;
 
     tpose::quit();
     return 0;

@@ -30,7 +30,7 @@ struct EvalShape { int group, grid_e, grid_t; bool narrow; int path, grid_s, gri
 constexpr int kPathTable = 0, kPathTiles = 1;
 constexpr int kTileH = 64;
 // a sequence of evaluations (see issue_sequence) and its instantiated graph
-struct SeqKey { const EvalJob* jobs; int njobs; EvalShape shape; int kind, len, first_set; unsigned flags; double tol; };
+struct SeqKey { const EvalJob* jobs; int njobs; EvalShape shape; int kind, len, first_set; unsigned flags; double tol; const int* stop = nullptr; };
 struct SeqGraph { SeqKey key; cudaGraphExec_t exec; uint64_t stamp; };
 // one instantiated frame (tpose_cuda_frame with device-visible caller buffers: see frame_mapped)
 struct FrameGraph { const void* in; void* ten; void* cn; void* ca; void* out; int set, nt, np, slot, flavour; EvalShape shape; const EvalJob* job; cudaGraphExec_t exec; };
@@ -78,6 +78,8 @@ struct tpose_cuda_ctx {
     // run_state | err_state | wmask | pts share one allocation ("report"), so that what a run's caller reads
     // next -- verdict, watch mask, points -- comes back in a single copy
     unsigned char* report = nullptr; size_t report_pts_off = 0; unsigned char* h_report = nullptr;
+    int* d_h_report = nullptr; int* d_h_hist[4] = {nullptr, nullptr, nullptr, nullptr};   // device aliases of h_report / h_hist_* (k_run_out)
+    bool run_alias_known = false, hist_alias_known = false;
     unsigned char* wbuf = nullptr;    // wtri | whe, packed at the current NT: one upload
     unsigned* h_run_mask = nullptr; bool run_mask_valid = false;   // watch mask of the frame the last run stopped on
     // per-frame history of tpose_cuda_run (tpose_cuda_set_history): device arrays + pinned host copies
@@ -526,36 +528,37 @@ static EvalShape make_shape(int group, int max_np, int max_ne, int max_nt, bool 
 }
 
 template <int G>
-static void launch_edges(const EvalJob* jobs, int njobs, const EvalShape& sh, int set, unsigned flags, double tol, int frame, cudaStream_t st)
+static void launch_edges(const EvalJob* jobs, int njobs, const EvalShape& sh, int set, unsigned flags, double tol, int frame, cudaStream_t st, const int* stop)
 {
     const dim3 grid(sh.grid_e + 1, njobs);   // + the service block
-    if (sh.narrow) k_edges<G, unsigned><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame);
-    else k_edges<G, unsigned long long><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame);
+    if (sh.narrow) k_edges<G, unsigned><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame, stop);
+    else k_edges<G, unsigned long long><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame, stop);
 }
 
 // one evaluation of every job: k_edges (or k_setup + k_tiles) then k_corners
+// `stop`: the stop flag of a single-job run (run_state), or null
 static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int set, unsigned flags, double tol, int frame, cudaStream_t st,
-                        cudaEvent_t mid = nullptr, cudaEvent_t mid0 = nullptr)
+                        cudaEvent_t mid = nullptr, cudaEvent_t mid0 = nullptr, const int* stop = nullptr)
 {
     if (sh.path == kPathTiles) {
         k_setup<kTileH><<<dim3(sh.grid_s + 1, njobs), kSetupThreads, 0, st>>>(jobs, set, flags, tol, frame);   // + the service block
         if (mid0) cudaEventRecord(mid0, st);
         k_tiles<kTileH><<<dim3(sh.grid_tiles, njobs), kTileThreads, tile_smem_bytes<kTileH>(), st>>>(jobs, flags);
         if (mid) cudaEventRecord(mid, st);
-        k_corners<EdgeRec><<<dim3(sh.grid_t + sh.grid_b, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame, sh.grid_b);   // (k_tiles adds 64-bit words)
+        k_corners<EdgeRec><<<dim3(sh.grid_t + sh.grid_b, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame, sh.grid_b, stop);   // (k_tiles adds 64-bit words)
         return;
     }
     switch (sh.group) {
-    case 1: launch_edges<1>(jobs, njobs, sh, set, flags, tol, frame, st); break;
-    case 2: launch_edges<2>(jobs, njobs, sh, set, flags, tol, frame, st); break;
-    case 4: launch_edges<4>(jobs, njobs, sh, set, flags, tol, frame, st); break;
-    case 8: launch_edges<8>(jobs, njobs, sh, set, flags, tol, frame, st); break;
-    case 16: launch_edges<16>(jobs, njobs, sh, set, flags, tol, frame, st); break;
-    default: launch_edges<32>(jobs, njobs, sh, set, flags, tol, frame, st); break;
+    case 1: launch_edges<1>(jobs, njobs, sh, set, flags, tol, frame, st, stop); break;
+    case 2: launch_edges<2>(jobs, njobs, sh, set, flags, tol, frame, st, stop); break;
+    case 4: launch_edges<4>(jobs, njobs, sh, set, flags, tol, frame, st, stop); break;
+    case 8: launch_edges<8>(jobs, njobs, sh, set, flags, tol, frame, st, stop); break;
+    case 16: launch_edges<16>(jobs, njobs, sh, set, flags, tol, frame, st, stop); break;
+    default: launch_edges<32>(jobs, njobs, sh, set, flags, tol, frame, st, stop); break;
     }
     if (mid) cudaEventRecord(mid, st);
-    if (sh.narrow) k_corners<EdgeRecNarrow><<<dim3(sh.grid_t + sh.grid_b, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame, sh.grid_b);
-    else k_corners<EdgeRec><<<dim3(sh.grid_t + sh.grid_b, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame, sh.grid_b);
+    if (sh.narrow) k_corners<EdgeRecNarrow><<<dim3(sh.grid_t + sh.grid_b, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame, sh.grid_b, stop);
+    else k_corners<EdgeRec><<<dim3(sh.grid_t + sh.grid_b, njobs), kCornerThreads, 0, st>>>(jobs, set, flags, frame, sh.grid_b, stop);
 }
 static int launches_per_eval(const EvalShape& sh) { return sh.path == kPathTiles ? 3 : 2; }
 
@@ -577,13 +580,13 @@ static void issue_direct(const SeqKey& k, cudaStream_t st, cudaEvent_t mid = nul
             if (j > 0) f |= EV_CHECK_PREV;
             if (j == k.len - 1) f |= EV_FINAL;
         }
-        launch_eval(k.shape, k.jobs, k.njobs, (k.first_set + j) & 1, f, k.tol, k.kind == 1 ? j : -1, st, mid, mid0);
+        launch_eval(k.shape, k.jobs, k.njobs, (k.first_set + j) & 1, f, k.tol, k.kind == 1 ? j : -1, st, mid, mid0, k.stop);
     }
 }
 
 static bool same_key(const SeqKey& a, const SeqKey& b)
 {
-    return a.jobs == b.jobs && a.njobs == b.njobs && a.kind == b.kind && a.len == b.len && a.first_set == b.first_set &&
+    return a.jobs == b.jobs && a.njobs == b.njobs && a.kind == b.kind && a.len == b.len && a.first_set == b.first_set && a.stop == b.stop &&
            a.flags == b.flags && a.tol == b.tol && a.shape.group == b.shape.group && a.shape.grid_e == b.shape.grid_e &&
            a.shape.grid_t == b.shape.grid_t && a.shape.narrow == b.shape.narrow && a.shape.path == b.shape.path &&
            a.shape.grid_s == b.shape.grid_s && a.shape.grid_tiles == b.shape.grid_tiles && a.shape.grid_b == b.shape.grid_b;
@@ -806,6 +809,28 @@ __global__ void __launch_bounds__(256) k_frame_out(FrameOut f)
     if (f.h_pts) copy_words(reinterpret_cast<const int*>(f.pts), reinterpret_cast<int*>(f.h_pts), 2 * f.np, tid, nthreads);
 }
 
+// What a run's caller reads -- the verdict block (run_state | err_state | watch mask | points) and, with the history
+// on, the frames the run actually took (RS_STEPS of them, not max_steps) -- pushed into the context's page-locked
+// host buffers by one kernel behind the run instead of one to five copy-engine operations.
+struct RunOut {
+    const int* report; int* h_report; int report_words;
+    const int* run_state;
+    const int* pts; const int* ten; const int* err; const int* mask;      // d_hist_* (null: no history)
+    int* h_pts; int* h_ten; int* h_err; int* h_mask;
+    int np, nt, words;
+};
+__global__ void __launch_bounds__(256) k_run_out(RunOut r)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    copy_words(r.report, r.h_report, r.report_words, tid, nthreads);
+    if (!r.pts) return;
+    const int done = r.run_state[RS_STEPS];
+    copy_words(r.pts, r.h_pts, 2 * r.np * done, tid, nthreads);
+    copy_words(r.ten, r.h_ten, r.nt * done, tid, nthreads);
+    copy_words(r.err, r.h_err, done, tid, nthreads);
+    copy_words(r.mask, r.h_mask, r.words * done, tid, nthreads);
+}
+
 // the device-side alias of a host pointer if the memory is page-locked and mapped, else nullptr
 static void* device_alias(const void* host)
 {
@@ -898,7 +923,8 @@ extern "C" int tpose_cuda_frame(tpose_cuda_ctx* ctx, int slot, int flavour, cons
 static int issue_run(tpose_cuda_ctx* lead, const EvalJob* jobs, int njobs, const EvalShape& sh, int first_set,
                      int flavour, int max_steps, double rel_tol, unsigned extra_flags = 0u)
 {
-    return issue_sequence(lead, SeqKey{jobs, njobs, sh, 1, max_steps + 1, first_set, fused_flags(flavour) | EV_HONOUR_STOP | extra_flags, rel_tol});
+    return issue_sequence(lead, SeqKey{jobs, njobs, sh, 1, max_steps + 1, first_set, fused_flags(flavour) | EV_HONOUR_STOP | extra_flags, rel_tol,
+                                       njobs == 1 ? lead->run_state : nullptr});
 }
 
 extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int max_steps, double rel_tol,
@@ -918,29 +944,53 @@ extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int ma
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->hist_np_frames = 0;
-    if (hist) {     // every frame the run may have taken, in the same synchronisation as the verdict
-        const size_t f = (size_t)max_steps, words = ((size_t)ctx->NT + 31) / 32;
-        CK(cudaMemcpyAsync(ctx->h_hist_pts, ctx->d_hist_pts, sizeof(float2) * ctx->NP * f, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->h_hist_ten, ctx->d_hist_ten, sizeof(int) * ctx->NT * f, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->h_hist_err, ctx->d_hist_err, sizeof(float) * f, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->h_hist_mask, ctx->d_hist_mask, sizeof(unsigned) * words * f, cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->hist_np = ctx->NP; ctx->hist_nt = ctx->NT;
-    }
     int rs[4]; float es[4];
     if (!ctx->h_report && cudaHostAlloc((void**)&ctx->h_report, ctx->report_pts_off + sizeof(float2) * (size_t)ctx->maxP, cudaHostAllocDefault) != cudaSuccess) {
         (void)cudaGetLastError(); ctx->h_report = nullptr;
     }
-    if (ctx->h_report) {
-        // verdict + watch mask + points in one copy (the mask region is sized for maxT: a few KB)
-        CK(cudaMemcpyAsync(ctx->h_report, ctx->report, ctx->report_pts_off + sizeof(float2) * (size_t)ctx->NP, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hist) { ctx->hist_np = ctx->NP; ctx->hist_nt = ctx->NT; }
+    // the device-visible aliases of the context's own page-locked buffers (looked up once)
+    if (!ctx->run_alias_known) {
+        ctx->run_alias_known = true;
+        ctx->d_h_report = (int*)device_alias(ctx->h_report);
+    }
+    if (hist && !ctx->hist_alias_known) {
+        ctx->hist_alias_known = true;
+        ctx->d_h_hist[0] = (int*)device_alias(ctx->h_hist_pts); ctx->d_h_hist[1] = (int*)device_alias(ctx->h_hist_ten);
+        ctx->d_h_hist[2] = (int*)device_alias(ctx->h_hist_err); ctx->d_h_hist[3] = (int*)device_alias(ctx->h_hist_mask);
+    }
+    const bool pushed = ctx->d_h_report && (!hist || (ctx->d_h_hist[0] && ctx->d_h_hist[1] && ctx->d_h_hist[2] && ctx->d_h_hist[3]));
+    const size_t report_bytes = ctx->report_pts_off + sizeof(float2) * (size_t)ctx->NP;      // (a multiple of 8)
+    if (pushed) {
+        RunOut r{(const int*)ctx->report, ctx->d_h_report, (int)(report_bytes / 4), ctx->run_state,
+                 hist ? (const int*)ctx->d_hist_pts : nullptr, (const int*)ctx->d_hist_ten, (const int*)ctx->d_hist_err, (const int*)ctx->d_hist_mask,
+                 ctx->d_h_hist[0], ctx->d_h_hist[1], ctx->d_h_hist[2], ctx->d_h_hist[3], ctx->NP, ctx->NT, (ctx->NT + 31) / 32};
+        k_run_out<<<hist ? 32 : 4, 256, 0, ctx->stream>>>(r);
+        ctx->launches++;
+        CK(cudaGetLastError());
         CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        if (hist) {     // every frame the run may have taken, in the same synchronisation as the verdict
+            const size_t f = (size_t)max_steps, words = ((size_t)ctx->NT + 31) / 32;
+            CK(cudaMemcpyAsync(ctx->h_hist_pts, ctx->d_hist_pts, sizeof(float2) * ctx->NP * f, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->h_hist_ten, ctx->d_hist_ten, sizeof(int) * ctx->NT * f, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->h_hist_err, ctx->d_hist_err, sizeof(float) * f, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->h_hist_mask, ctx->d_hist_mask, sizeof(unsigned) * words * f, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (ctx->h_report) {
+            // verdict + watch mask + points in one copy (the mask region is sized for maxT: a few KB)
+            CK(cudaMemcpyAsync(ctx->h_report, ctx->report, report_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        } else {
+            CK(cudaMemcpyAsync(rs, ctx->run_state, sizeof rs, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(es, ctx->err_state, sizeof es, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    if (ctx->h_report) {
         memcpy(rs, ctx->h_report, sizeof rs); memcpy(es, ctx->h_report + 16, sizeof es);
         ctx->h_run_mask = (unsigned*)(ctx->h_report + 32);
         ctx->h_run_pts = (float*)(ctx->h_report + ctx->report_pts_off);
-    } else {
-        CK(cudaMemcpyAsync(rs, ctx->run_state, sizeof rs, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(es, ctx->err_state, sizeof es, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
     }
     ctx->run_cache_valid = ctx->h_report != nullptr; ctx->run_toterr = es[0];
     ctx->run_mask_valid = !hist && ctx->h_report && ctx->watching && (rs[RS_TRIG] & kTrigTopology);
@@ -966,6 +1016,7 @@ extern "C" int tpose_cuda_set_history(tpose_cuda_ctx* ctx, int frames)
         if (ctx->h_hist_mask) cudaFreeHost(ctx->h_hist_mask);
         ctx->d_hist_pts = nullptr; ctx->d_hist_ten = nullptr; ctx->d_hist_err = nullptr; ctx->d_hist_mask = nullptr;
         ctx->h_hist_pts = nullptr; ctx->h_hist_ten = nullptr; ctx->h_hist_err = nullptr; ctx->h_hist_mask = nullptr;
+        ctx->hist_alias_known = false;
         ctx->hist_cap = 0;
         const size_t f = (size_t)frames, words = ((size_t)ctx->maxT + 31) / 32;
         CK(cudaMalloc((void**)&ctx->d_hist_pts, sizeof(float2) * ctx->maxP * f));

@@ -16,7 +16,7 @@
 // A step can also carry the host-side checks of the PREVIOUS frame (EV_CHECK_PREV), so that a run
 // of frames needs no host round trip and no serial check between frames:
 //   * geterr (source/triangulation.hpp:653-674) over the previous frame's base energies, by one
-//     thread of k_edges' service block, overlapped with the edge walks;
+//     warp of k_edges' service block (one in-order chain of float32 additions), overlapped with the edge walks;
 //   * a conservative test of the per-frame topology edits of software/triangulate/main.cpp:316-346
 //     (prune / >0.8*pi flip / short-edge collapse) on the host's ("watch") topology at the current
 //     points, by the other threads of the service block.
@@ -181,20 +181,37 @@ __device__ int watch_triangle(const EvalJob& J, int t)
     return 0;
 }
 
-// geterr (source/triangulation.hpp:653-674): float32 running sum of the base energies in index
-// order -- order matters, so it is one thread.
-__device__ void geterr_serial(const int* __restrict__ ten_base, int nt, float* state, double rel_tol)
+// geterr (source/triangulation.hpp:653-674): float32 running sum of the base energies in index order.  Order
+// matters (float addition is not associative), so the additions are one dependent chain -- but nothing else has
+// to be serial: one WARP runs it.  Every lane loads its share of the next 256 energies (coalesced, converted to
+// float, issued one round ahead of their use), and all lanes add the same 256 values in index order, fetching
+// each from the lane that holds it with a shuffle.  The chain then costs one FADD latency per element (~2 ns)
+// instead of a dependent global load every few elements (one thread: 28 us at 3 000 triangles, measured --
+// three times the rest of the step, and k_edges cannot end before its service block does).
+// Elements past nt are +0.0f: s + 0 = s exactly (s is never -0: it starts at +0 and a zero sum rounds to +0).
+__device__ void geterr_warp(const int* __restrict__ ten_base, int nt, float* state, double rel_tol, int lane)
 {
+    constexpr int K = 8;                       // registers per lane and round: 32 * K energies per round
+    float cur[K], nxt[K];
+    auto load = [&](int base, float (&r)[K]) {
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int i = base + 32 * j + lane;
+            r[j] = i < nt ? (float)__ldcg(ten_base + i) : 0.0f;
+        }
+    };
     float newerr = 0.0f;
-    int i = 0;
-    for (; i + 4 <= nt; i += 4) {
-        const int4 v = *reinterpret_cast<const int4*>(ten_base + i);
-        newerr = __fadd_rn(newerr, (float)v.x);
-        newerr = __fadd_rn(newerr, (float)v.y);
-        newerr = __fadd_rn(newerr, (float)v.z);
-        newerr = __fadd_rn(newerr, (float)v.w);
+    load(0, cur);
+    for (int base = 0; base < nt; base += 32 * K) {
+        if (base + 32 * K < nt) load(base + 32 * K, nxt);
+#pragma unroll
+        for (int j = 0; j < K; j++)
+#pragma unroll
+            for (int l = 0; l < 32; l++) newerr = __fadd_rn(newerr, __shfl_sync(0xffffffffu, cur[j], l));
+#pragma unroll
+        for (int j = 0; j < K; j++) cur[j] = nxt[j];
     }
-    for (; i < nt; i++) newerr = __fadd_rn(newerr, (float)ten_base[i]);
+    if (lane != 0) return;
     const float tot = state[0];
     const float rel = __fdiv_rn(__fsub_rn(tot, newerr), tot);
     state[0] = newerr;
@@ -206,7 +223,7 @@ __device__ void geterr_serial(const int* __restrict__ ten_base, int nt, float* s
 
 // ---- the service block (shared by k_edges and k_setup) ---------------------------------------------
 // Pulls the static index arrays k_corners is about to chase through into L2, then runs the previous
-// frame's host-side checks: geterr (one thread) and the topology watch (the others).  See eval.cuh.
+// frame's host-side checks: geterr (the last warp) and the topology watch (the others).
 __device__ void service_block(EvalJob& J, int set, unsigned flags, double rel_tol, int frame, int tid, int nthreads, bool single_job)
 {
     if (!(flags & EV_FINAL) && single_job) {
@@ -226,12 +243,12 @@ __device__ void service_block(EvalJob& J, int set, unsigned flags, double rel_to
     unsigned* const mask = hist ? J.hist_mask + (size_t)(frame - 1) * words : J.wmask;
     if (J.wtri || hist) for (int w = tid; w < words; w += nthreads) mask[w] = 0u;   // (no watch topology: an empty mask)
     __syncthreads();
-    if (tid == nthreads - 1) {
-        geterr_serial(J.ten[set ^ 1], J.NT, J.err_state, rel_tol);
-        if (hist) J.hist_err[frame - 1] = J.err_state[0];
+    if (tid >= nthreads - 32) {               // the last warp: geterr
+        geterr_warp(J.ten[set ^ 1], J.NT, J.err_state, rel_tol, tid & 31);
+        if (hist && tid == nthreads - 32) J.hist_err[frame - 1] = J.err_state[0];
     } else if (J.wtri) {
         bool hit = false;
-        for (int t = tid; t < J.NT; t += nthreads - 1) {
+        for (int t = tid; t < J.NT; t += nthreads - 32) {
             const int code = watch_triangle(J, t);
             if (code) atomicOr(&mask[t >> 5], 1u << (t & 31));
             hit |= (flags & EV_HISTORY) ? code == 2 : code != 0;
@@ -338,14 +355,17 @@ __device__ __forceinline__ void walk_edge(EdgeWalk& w, const uint4* __restrict__
                                      n, odd, sr, sg, sb, s2);
 }
 
-// G lanes per (edge, move) item.  The last block of each job's row is the service block.
+// G lanes per (edge, move) item.  One block of each job's row is the service block.
 template <int G, typename ACC>
 __global__ void __launch_bounds__(kEdgeThreads)
-k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_tol, int frame)
+k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_tol, int frame, const int* __restrict__ stop_flag)
 {
     __shared__ EvalJob J;
     const int tid = threadIdx.x;
     TL(0, 0);
+    // a single-job run hands its stop flag over as an argument: the launches behind the stop of a flat chain
+    // then cost one load, not a job record and a dependent load
+    if (stop_flag && __ldcg(stop_flag)) return;
     if (tid < (int)(sizeof(EvalJob) / sizeof(int)))
         reinterpret_cast<int*>(&J)[tid] = reinterpret_cast<const int*>(jobs + blockIdx.y)[tid];
     __syncthreads();
@@ -353,13 +373,21 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
     if ((flags & EV_HONOUR_STOP) && __ldcg(&J.run_state[RS_STOP])) return;
     set ^= J.flip;
 
-    // the last evaluation of a run only carries the checks of the last frame: nothing to integrate
-    if ((flags & EV_FINAL) && blockIdx.x != gridDim.x - 1) return;
+    // One block of each job's row is the service block.  For a single job it is block 0: the in-order float sum of
+    // geterr is the longest dependent chain of the launch, so it is dispatched first and runs under the walkers (as
+    // the last block it started when the first walker finished, and the kernel waited for it: 25.8 -> 23.2 us per
+    // frame of a run at 1080p / 3000 triangles).  In a batch the other jobs' walkers cover it anyway and first place
+    // costs 10-15 % (config 5, measured), so there it stays the last block of its row.
+    const int service = gridDim.y == 1 ? 0 : (int)gridDim.x - 1;
 
-    if (blockIdx.x == gridDim.x - 1) {
+    // the last evaluation of a run only carries the checks of the last frame: nothing to integrate
+    if ((flags & EV_FINAL) && (int)blockIdx.x != service) return;
+
+    if ((int)blockIdx.x == service) {
         service_block(J, set, flags, rel_tol, frame, tid, kEdgeThreads, gridDim.y == 1);
         return;
     }
+    const int worker = (int)blockIdx.x - ((int)blockIdx.x > service), nworkers = (int)gridDim.x - 1;
 
     constexpr int kItemsPerBlock = kEdgeThreads / G;
     const int lane = tid % G;
@@ -367,7 +395,7 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
     const Xform xf{J.ratio, 0.5f * (float)J.W, 0.5f * (float)J.H, 256 * J.H};
     // the grid does not depend on the mesh size (so a captured graph survives topology changes):
     // blocks stride over the items
-    for (int base = blockIdx.x * kItemsPerBlock; base < nitems; base += (gridDim.x - 1) * kItemsPerBlock) {
+    for (int base = worker * kItemsPerBlock; base < nitems; base += nworkers * kItemsPerBlock) {
         const int item = base + tid / G;
         unsigned n = 0, odd = 0; ACC sr = 0, sg = 0, sb = 0; unsigned long long s2 = 0;
         int sign = 0;
@@ -527,11 +555,12 @@ __device__ __forceinline__ int eval_variant(const EvalJob& J, unsigned flags, in
 
 template <typename REC>
 __global__ void __launch_bounds__(kCornerThreads)
-k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame, int base_blocks)
+k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame, int base_blocks, const int* __restrict__ stop_flag)
 {
     __shared__ EvalJob J;
     const int tid = threadIdx.x;
     TL(1, 0);
+    if (stop_flag && __ldcg(stop_flag)) return;       // (see k_edges; a block that sees the stop THIS launch raised skips work that is discarded anyway)
     if (tid < (int)(sizeof(EvalJob) / sizeof(int)))
         reinterpret_cast<int*>(&J)[tid] = reinterpret_cast<const int*>(jobs + blockIdx.y)[tid];
     __syncthreads();

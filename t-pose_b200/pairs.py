@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-HOST_SO = os.path.join(_HERE, "libtpose_host.so")
+HOST_SO = os.environ.get("TPOSE_HOST_LIB") or os.path.join(_HERE, "libtpose_host.so")   # override: development experiments
 _host = None
 
 
