@@ -321,6 +321,7 @@ def run_config5(args, pkg, synth, rank, world, local, dist, barrier, max_over_ra
     barrier(ctx)
     t0 = time.perf_counter()
     frames, levels = ps.run(tol=1e-6, level_cap=cap)
+    where = ps.timing()            # rank 0's split of its own compute time
     packed = [ps.packed(i) for i in range(len(share))]
     t_compute = time.perf_counter() - t0
     length = len(packed[0]) if packed else 0
@@ -347,6 +348,7 @@ def run_config5(args, pkg, synth, rank, world, local, dist, barrier, max_over_ra
                            "triangulate(F,K,A,B), all pairs of a rank in shared launches, one process per GPU",
                "pairs_per_s": total / t_total, "seconds": t_total, "compute_seconds_max_rank": t_compute,
                "frames_per_pair": int(frames[0]), "levels_per_pair": int(levels[0]), "pairs_per_rank": len(share),
+               "rank0_seconds_in": where,
                "gather": {"collective": "tpose_b200.shard.gather_units: torch.distributed.gather over NCCL (payload + lengths), inside the timed region"
                                         if dist is not None else "single rank: nothing to gather",
                           "bytes_per_pair": int(4 * length), "bytes_total": int(4 * length * total), "ms": gather_ms},

@@ -1772,7 +1772,7 @@ extern "C" int tpose_cuda_carry(int device, const int32_t* tri_xyzw, int nt, con
     MCK(cudaMemcpyAsync(dF, from_xy, sizeof(float2) * nv, cudaMemcpyHostToDevice, st));
     MCK(cudaMemcpyAsync(dTo, to_xy, sizeof(float2) * nv, cudaMemcpyHostToDevice, st));
     MCK(cudaMemcpyAsync(dP, pts_xy, sizeof(float2) * npts, cudaMemcpyHostToDevice, st));
-    k_carry<<<(npts + kCarryThreads - 1) / kCarryThreads, kCarryThreads, 0, st>>>(dT, nt, dF, dTo, dP, npts, ratio);
+    k_carry<<<(int)(((long long)npts * kCarryLanes + kCarryThreads - 1) / kCarryThreads), kCarryThreads, 0, st>>>(dT, nt, dF, dTo, dP, npts, ratio);
     MCK(cudaGetLastError());
     MCK(cudaMemcpyAsync(pts_xy, dP, sizeof(float2) * npts, cudaMemcpyDeviceToHost, st));
     MCK(cudaStreamSynchronize(st));

@@ -265,6 +265,12 @@ void tph_pairs_run(void* h, double tol, long level_cap, int with_mview, long* fr
     if (with_mview) tpose::pairs::fundamental_and_points(js, s->device);
     for (size_t i = 0; i < js.size(); i++) { if (frames) frames[i] = js[i]->frames; if (levels) levels[i] = js[i]->levels; }
 }
+// wall seconds of the last tph_pairs_run: [batch_run, level switches on the host, F + DLT, runs, frames asked, frames run]
+void tph_pairs_timing(double* out6)
+{
+    const auto& t = tpose::pairs::last_timing;
+    out6[0] = t.batch_run; out6[1] = t.level_switch; out6[2] = t.mview; out6[3] = (double)t.runs; out6[4] = (double)t.frames_asked; out6[5] = (double)t.frames_run;
+}
 // sizes of pair i's results: [NP of A, NP of B, matches]
 void tph_pairs_sizes(void* h, int i, int* out3)
 {

@@ -94,6 +94,14 @@ class PairSet:
         host().tph_pairs_run(self._h, C.c_double(tol), C.c_long(level_cap), int(mview), fr, lv)
         return list(fr), list(lv)
 
+    @staticmethod
+    def timing():
+        """Where the wall time of the last run() went: seconds in tpose_cuda_batch_run, in the host's level switches
+        (reversewarp, stack I/O, uploads) and in F + DLT; batch_run calls, frames asked of / run by them."""
+        t = (C.c_double * 6)()
+        host().tph_pairs_timing(t)
+        return dict(batch_run_s=t[0], level_switch_s=t[1], mview_s=t[2], runs=int(t[3]), frames_asked=int(t[4]), frames_run=int(t[5]))
+
     def result(self, i):
         """dict(ptsA, optsA, ptsB, optsB (finest level's vertex buffers), F (3,3), X (matches,4))."""
         sz = (C.c_int * 3)()
