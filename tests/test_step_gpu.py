@@ -507,3 +507,23 @@ def test_eval_list_equals_rows_of_the_full_evaluation(cuda_pkg, synth, O, kernel
     with pytest.raises(cuda_pkg.TposeCudaError):
         ctx.eval_list(0, np.array([[0, 1, 99999, 0]], np.int32))
     ctx.close()
+
+
+def test_run_results_reach_the_host_without_copy_engine_operations(cuda_pkg, synth):
+    """A run's verdict block and recorded frames are pushed into the context's page-locked buffers by one kernel
+    behind the chain (k_run_out): 2 * (max_steps + 1) evaluation launches + 1, with and without the history."""
+    w, h = 160, 120
+    ratio = w / h
+    img = synth.make_image(w, h, seed=2)
+    pts, tri, he = synth.mesh_for(150, ratio)
+    c = _ctx(cuda_pkg)
+    c.set_image(0, img); c.upload(pts, tri, ratio)
+    per_eval = 3 if c.kernel_path() == "tiles" else 2
+    for hist in (0, 8):
+        c.set_history(hist)
+        c.run(0, cuda_pkg.TRIANGULATE, 5, 1e-30)
+        n0 = c.launch_count()
+        done, _, _ = c.run(0, cuda_pkg.TRIANGULATE, 5, 1e-30)
+        assert done == 5
+        assert c.launch_count() - n0 == per_eval * 6 + 1
+    c.close()
