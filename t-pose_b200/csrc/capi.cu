@@ -26,7 +26,7 @@ using namespace tpose_dev;
 // Launch geometry of one evaluation.  Grid sizes are quantised (power of two, at most one full
 // wave) and the kernels stride, so a captured sequence stays valid while the mesh grows.
 // path: 0 = row-prefix table gathers (k_edges), 1 = TMA-staged tiles (k_setup + k_tiles)
-struct EvalShape { int group, grid_e, grid_t; bool narrow; int path, grid_s, grid_tiles; int grid_b; };
+struct EvalShape { int group, grid_e, grid_t; bool narrow; int path, grid_s, grid_tiles; int grid_b; bool dense = false; };
 constexpr int kPathTable = 0, kPathTiles = 1;
 constexpr int kTileH = 64;
 // a sequence of evaluations (see issue_sequence) and its instantiated graph
@@ -509,15 +509,18 @@ static int quantised_grid(long long blocks_needed, int cap = kMaxGridBlocks)
     return g < cap ? g : cap;
 }
 
-static EvalShape make_shape(int group, int max_np, int max_ne, int max_nt, bool narrow, int path, int max_tiles)
+static EvalShape make_shape(int group, int max_np, int max_ne, int max_nt, bool narrow, int path, int max_tiles, bool single_job)
 {
     const int per_block = kEdgeThreads / group;
+    // k_edges' shape (eval.cuh): the dense one where it spares a single image a second pass through the chain
+    const long long edge_blocks = ((long long)max_ne * kEdgeMoves + per_block - 1) / per_block;
+    const bool dense = single_job && path == kPathTable && edge_blocks > kSMs * kEdgeBlocksWide && edge_blocks <= kSMs * kEdgeBlocksDense;
     // k_corners: blocks for the base variants in proportion to NT (one variant per thread), and vertex blocks up to
     // what is resident together with them, so that neither part of the grid takes a second turn on a busy SM
     const int base_blocks = quantised_grid((max_nt + kCornerThreads - 1) / kCornerThreads, 128) < 16 ? 16
                             : quantised_grid((max_nt + kCornerThreads - 1) / kCornerThreads, 128);
-    EvalShape sh{group, quantised_grid(((long long)max_ne * kEdgeMoves + per_block - 1) / per_block),
-                 quantised_grid((max_np + kCornerWarps - 1) / kCornerWarps, kSMs * kCornerBlocksPerSM - base_blocks), narrow, path, 0, 0, base_blocks};
+    EvalShape sh{group, quantised_grid(edge_blocks, kSMs * (dense ? kEdgeBlocksDense : kEdgeBlocksWide)),
+                 quantised_grid((max_np + kCornerWarps - 1) / kCornerWarps, kSMs * kCornerBlocksPerSM - base_blocks), narrow, path, 0, 0, base_blocks, dense};
     if (path == kPathTiles) {
         // (group, grid_e and narrow do not exist on the tile path: keep them out of the graph key)
         sh.group = 1; sh.grid_e = 0; sh.narrow = true;
@@ -531,8 +534,13 @@ template <int G>
 static void launch_edges(const EvalJob* jobs, int njobs, const EvalShape& sh, int set, unsigned flags, double tol, int frame, cudaStream_t st, const int* stop)
 {
     const dim3 grid(sh.grid_e + 1, njobs);   // + the service block
-    if (sh.narrow) k_edges<G, unsigned><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame, stop);
-    else k_edges<G, unsigned long long><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame, stop);
+    if (sh.dense) {
+        if (sh.narrow) k_edges<G, unsigned, true><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame, stop);
+        else k_edges<G, unsigned long long, true><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame, stop);
+    } else {
+        if (sh.narrow) k_edges<G, unsigned, false><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame, stop);
+        else k_edges<G, unsigned long long, false><<<grid, kEdgeThreads, 0, st>>>(jobs, set, flags, tol, frame, stop);
+    }
 }
 
 // one evaluation of every job: k_edges (or k_setup + k_tiles) then k_corners
@@ -589,7 +597,7 @@ static bool same_key(const SeqKey& a, const SeqKey& b)
     return a.jobs == b.jobs && a.njobs == b.njobs && a.kind == b.kind && a.len == b.len && a.first_set == b.first_set && a.stop == b.stop &&
            a.flags == b.flags && a.tol == b.tol && a.shape.group == b.shape.group && a.shape.grid_e == b.shape.grid_e &&
            a.shape.grid_t == b.shape.grid_t && a.shape.narrow == b.shape.narrow && a.shape.path == b.shape.path &&
-           a.shape.grid_s == b.shape.grid_s && a.shape.grid_tiles == b.shape.grid_tiles && a.shape.grid_b == b.shape.grid_b;
+           a.shape.grid_s == b.shape.grid_s && a.shape.grid_tiles == b.shape.grid_tiles && a.shape.grid_b == b.shape.grid_b && a.shape.dense == b.shape.dense;
 }
 
 static int issue_sequence(tpose_cuda_ctx* ctx, const SeqKey& key)
@@ -699,7 +707,7 @@ static int sync_job(tpose_cuda_ctx* ctx, int slot, int flavour)
 static EvalShape shape_of(const tpose_cuda_ctx* ctx, int slot)
 {
     const ImageSlot& im = ctx->img[slot];
-    return make_shape(pick_group(ctx, ctx->NT, im.H), ctx->NP, ctx->NE, ctx->NT, narrow_sums(im.W, im.H), ctx->path, im.ntx * im.nty);
+    return make_shape(pick_group(ctx, ctx->NT, im.H), ctx->NP, ctx->NE, ctx->NT, narrow_sums(im.W, im.H), ctx->path, im.ntx * im.nty, true);
 }
 
 static int eval(tpose_cuda_ctx* ctx, int slot, int flavour, int set, unsigned flags, double tol = 0.0)
@@ -1162,7 +1170,7 @@ static int batch_prepare(tpose_cuda_ctx* const* ctxs, int n, const int* slots, i
     }
     CK(cudaMemcpyAsync(lead->batch_jobs, jobs.data(), sizeof(EvalJob) * n, cudaMemcpyHostToDevice, lead->stream));
     CK(cudaStreamSynchronize(lead->stream));   // `jobs` is a local
-    *shape = make_shape(valid_group(lead->group) ? lead->group : group_for(rows / n, items), mxp, mxe, mxn, narrow, lead->path, mxt);
+    *shape = make_shape(valid_group(lead->group) ? lead->group : group_for(rows / n, items), mxp, mxe, mxn, narrow, lead->path, mxt, false);
     return TPOSE_OK;
 }
 

@@ -285,13 +285,17 @@ template <typename T> __device__ __forceinline__ T shfl_xor_any(T v, int o) { re
 // Walks the rows of one edge (this lane's share: rows r, r+G, ...) and sums the table entries at
 // the crossings.  ACC is the accumulator type of the three colour sums: 32 bits are enough when
 // 255*W*H < 2^31 (every image up to 3840x2160), else 64.
-// Rows are taken kWalkBatch at a time: all loads of a batch are issued before the first one is
+// Rows are taken BATCH at a time: all loads of a batch are issued before the first one is
 // consumed, so a lane pays one memory latency per batch, not per row; whole batches first, then
 // one tail batch whose slots past the end of the edge read a zero entry.
-#ifndef TPOSE_WALK_BATCH
-#define TPOSE_WALK_BATCH 8
-#endif
-constexpr int kWalkBatch = TPOSE_WALK_BATCH;
+// k_edges exists in two shapes (capi.cu picks per launch):
+//   wide   batches of 8, 61-64 registers, 4 blocks per SM -- the default;
+//   dense  batches of 4, 48 registers, 5 blocks per SM: 740 resident blocks instead of 592.  For a single image whose
+//          items need more than 592 blocks but not more than 740 (1080p / 3 000 triangles: 641) the wide shape
+//          sends 49 blocks through the whole dependent chain a second time while the machine idles; the dense one
+//          takes everything in one pass (cold k_edges 16.4 -> 14.4 us, cold step +11 %, measured).
+constexpr int kWalkBatchWide = 8, kWalkBatchDense = 4;
+constexpr int kEdgeBlocksWide = 4, kEdgeBlocksDense = 5;
 
 // A table entry through the read-only path with the L2 fetch size pinned to 64 bytes (SASS: LDG.E.LTC64B.128.CONSTANT).
 // A plain load that misses L2 makes it fetch the whole 128-byte line from DRAM (measured on B200 with a strided
@@ -305,18 +309,18 @@ __device__ __forceinline__ uint4 ldg_entry(const uint4* p)
     return v;
 }
 
-// one batch of kWalkBatch rows.  TAIL: the edge may end inside the batch -- a slot past its end reads entry 0
+// one batch of BATCH rows.  TAIL: the edge may end inside the batch -- a slot past its end reads entry 0
 // (column 0 of row 0: an all-zero prefix), an unconditional load of zeros instead of a predicated load into
 // zeroed registers; full batches carry no per-slot test at all.
-template <int G, typename ACC, typename REM, bool TAIL>
+template <int G, int BATCH, typename ACC, typename REM, bool TAIL>
 __device__ __forceinline__ void walk_batch(const int rr, const int r_end, int& q, const int dq, REM& rem, const REM den, const REM dr,
                                            const uint4* __restrict__ table, int& row, const int rstep, const int W,
                                            unsigned& n, unsigned& odd, ACC& sr, ACC& sg, ACC& sb, unsigned long long& s2)
 {
-    uint4 e[kWalkBatch];
-    int c[kWalkBatch];
+    uint4 e[BATCH];
+    int c[BATCH];
 #pragma unroll
-    for (int u = 0; u < kWalkBatch; u++) {
+    for (int u = 0; u < BATCH; u++) {
         const bool on = !TAIL || rr + u * G < r_end;
         const int cc = min(max(q, 0), W);
         c[u] = on ? cc : 0;
@@ -326,38 +330,38 @@ __device__ __forceinline__ void walk_batch(const int rr, const int r_end, int& q
         row += rstep;
     }
 #pragma unroll
-    for (int u = 0; u < kWalkBatch; u++) {
+    for (int u = 0; u < BATCH; u++) {
         n += (unsigned)c[u]; odd += e[u].x >> 20; sr += (ACC)(e[u].x & 0xFFFFFu);
         sg += (ACC)e[u].y; sb += (ACC)e[u].z; s2 += e[u].w;
     }
 }
 
-template <int G, typename ACC, typename REM>
+template <int G, int BATCH, typename ACC, typename REM>
 __device__ __forceinline__ void walk_rows(int rr, const int r_end, int q, const int dq, REM rem, const REM den, const REM dr,
                                           const uint4* __restrict__ table, int row, const int rstep, const int W,
                                           unsigned& n, unsigned& odd, ACC& sr, ACC& sg, ACC& sb, unsigned long long& s2)
 {
-    for (; rr + (kWalkBatch - 1) * G < r_end; rr += kWalkBatch * G)
-        walk_batch<G, ACC, REM, false>(rr, r_end, q, dq, rem, den, dr, table, row, rstep, W, n, odd, sr, sg, sb, s2);
+    for (; rr + (BATCH - 1) * G < r_end; rr += BATCH * G)
+        walk_batch<G, BATCH, ACC, REM, false>(rr, r_end, q, dq, rem, den, dr, table, row, rstep, W, n, odd, sr, sg, sb, s2);
     if (rr < r_end)
-        walk_batch<G, ACC, REM, true>(rr, r_end, q, dq, rem, den, dr, table, row, rstep, W, n, odd, sr, sg, sb, s2);
+        walk_batch<G, BATCH, ACC, REM, true>(rr, r_end, q, dq, rem, den, dr, table, row, rstep, W, n, odd, sr, sg, sb, s2);
 }
 
-template <int G, typename ACC>
+template <int G, int BATCH, typename ACC>
 __device__ __forceinline__ void walk_edge(EdgeWalk& w, const uint4* __restrict__ table, int pitch, int W,
                                           unsigned& n, unsigned& odd, ACC& sr, ACC& sg, ACC& sb, unsigned long long& s2)
 {
     if (w.den < (1ll << 30))                   // every on-screen edge: remainders fit 32 bits
-        walk_rows<G, ACC, int>(w.r, w.r_end, w.q, w.dq, (int)w.rem, (int)w.den, (int)w.dr, table, w.r * pitch, G * pitch, W,
+        walk_rows<G, BATCH, ACC, int>(w.r, w.r_end, w.q, w.dq, (int)w.rem, (int)w.den, (int)w.dr, table, w.r * pitch, G * pitch, W,
                                n, odd, sr, sg, sb, s2);
     else
-        walk_rows<G, ACC, long long>(w.r, w.r_end, w.q, w.dq, w.rem, w.den, w.dr, table, w.r * pitch, G * pitch, W,
+        walk_rows<G, BATCH, ACC, long long>(w.r, w.r_end, w.q, w.dq, w.rem, w.den, w.dr, table, w.r * pitch, G * pitch, W,
                                      n, odd, sr, sg, sb, s2);
 }
 
 // G lanes per (edge, move) item.  One block of each job's row is the service block.
-template <int G, typename ACC>
-__global__ void __launch_bounds__(kEdgeThreads)
+template <int G, typename ACC, bool DENSE>
+__global__ void __launch_bounds__(kEdgeThreads, DENSE ? kEdgeBlocksDense : kEdgeBlocksWide)
 k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_tol, int frame, const int* __restrict__ stop_flag)
 {
     __shared__ EvalJob J;
@@ -416,7 +420,7 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
 #ifdef TPOSE_TIMELINE
             if (w.q != 0x7fffffff) TL(0, 3);
 #endif
-            walk_edge<G, ACC>(w, J.table, J.pitch, J.W, n, odd, sr, sg, sb, s2);
+            walk_edge<G, DENSE ? kWalkBatchDense : kWalkBatchWide, ACC>(w, J.table, J.pitch, J.W, n, odd, sr, sg, sb, s2);
 #ifdef TPOSE_TIMELINE
             if (n + s2 != 0x7fffffffffull) TL(0, 4);
 #endif
@@ -676,7 +680,7 @@ k_eval_list(const uint4* __restrict__ table, int pitch, int W, int H, const floa
         EdgeWalk w;
         w.init(q[j], q[(j + 1) % 3], H, lane, 32);
         unsigned un = 0, uo = 0; ACC ur = 0, ug = 0, ub = 0; unsigned long long us2 = 0;
-        walk_edge<32, ACC>(w, table, pitch, W, un, uo, ur, ug, ub, us2);
+        walk_edge<32, kWalkBatchWide, ACC>(w, table, pitch, W, un, uo, ur, ug, ub, us2);
         const int sgn = w.sign;
         cnt += sgn * (int)un; odd += sgn * (int)uo;
         sr += sgn * (long long)ur; sg += sgn * (long long)ug; sb += sgn * (long long)ub; s2 += sgn * (long long)us2;
