@@ -457,11 +457,12 @@ static int rebuild_edges(tpose_cuda_ctx* ctx)
     tpose::edgeview::view& v = ctx->edge_view;
     if (!tpose::edgeview::build(ctx->tri_host.data(), nt, np, v, ctx->scratch_keys))
         return fail(ctx, TPOSE_ERR_ARG, "index buffer references a vertex outside [0,NP)");
-    CK(cudaMemcpyAsync(ctx->edges, v.edges.data(), sizeof(int2) * v.ne, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->tri_edges, v.tri_edges.data(), sizeof(int4) * nt, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->corner_off, v.corner_off.data(), sizeof(int) * (np + 1), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->corners, v.corners.data(), sizeof(int) * 3 * nt, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));   // the view's vectors are reused
+    // through the page-locked staging slots (the view's vectors are reused): no synchronisation here
+    int rc;
+    if ((rc = upload_bytes(ctx, ctx->edges, v.edges.data(), sizeof(int2) * v.ne)) != 0) return rc;
+    if ((rc = upload_bytes(ctx, ctx->tri_edges, v.tri_edges.data(), sizeof(int4) * nt)) != 0) return rc;
+    if ((rc = upload_bytes(ctx, ctx->corner_off, v.corner_off.data(), sizeof(int) * (np + 1))) != 0) return rc;
+    if ((rc = upload_bytes(ctx, ctx->corners, v.corners.data(), sizeof(int) * 3 * nt)) != 0) return rc;
     ctx->NE = v.ne; ctx->edges_np = np;
     ctx->edges_dirty = false;
     return TPOSE_OK;
