@@ -67,7 +67,8 @@ def run(cmd, timeout):
     dt = time.perf_counter() - t0
     if p.returncode != 0:
         raise RuntimeError(" ".join(cmd) + "\n" + p.stdout[-2000:] + p.stderr[-2000:])
-    return p.stdout.strip().splitlines()[-1], dt
+    # the program's summary: the "frames ..." line and the "runs ..." line under it
+    return " | ".join(p.stdout.strip().splitlines()[-2:]), dt
 
 
 res = {"quick": a.quick}
