@@ -66,7 +66,9 @@ int main(int argc, char* args[])
               << rep.idle_host_frames << ", exports " << rep.exports << ", " << tr.NT << " triangles, " << sec << " s ("
               << rep.s_device << " in tpose_cuda_run, " << rep.s_host << " in the host body), " << rep.frames / sec << " steps/s" << std::endl;
     std::cout << "runs " << rep.runs << ": " << rep.frames_asked << " frames asked, " << rep.frames_run << " run, " << rep.frames << " kept; "
-              << rep.resyncs << " runs cut short by a host edit; device-timed " << rep.ms_device_events / 1000.0 << " s" << std::endl;
+              << rep.resyncs << " runs cut short by a host edit; device-timed " << rep.ms_device_events / 1000.0 << " s; host body: "
+              << rep.s_fetch << " s recorded frame -> mesh, " << rep.s_edits << " per-frame edits, " << rep.s_converged << " converged frames, "
+              << rep.s_resync << " uploads after an edit" << std::endl;
 
     tpose::quit();
     return 0;
