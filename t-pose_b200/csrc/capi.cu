@@ -30,7 +30,7 @@ struct EvalShape { int group, grid_e, grid_t; bool narrow; int path, grid_s, gri
 constexpr int kPathTable = 0, kPathTiles = 1;
 constexpr int kTileH = 64;
 // a sequence of evaluations (see issue_sequence) and its instantiated graph
-struct SeqKey { const EvalJob* jobs; int njobs; EvalShape shape; int kind, len, first_set; unsigned flags; double tol; const int* stop = nullptr; };
+struct SeqKey { const EvalJob* jobs; int njobs; EvalShape shape; int kind, len, first_set; unsigned flags; double tol; Early early = Early{}; };
 struct SeqGraph { SeqKey key; cudaGraphExec_t exec; uint64_t stamp; };
 // one instantiated frame (tpose_cuda_frame with device-visible caller buffers: see frame_mapped)
 struct FrameGraph { const void* in; void* ten; void* cn; void* ca; void* out; int set, nt, np, slot, flavour; EvalShape shape; const EvalJob* job; cudaGraphExec_t exec; };
@@ -532,7 +532,7 @@ static EvalShape make_shape(int group, int max_np, int max_ne, int max_nt, bool 
 }
 
 template <int G>
-static void launch_edges(const EvalJob* jobs, int njobs, const EvalShape& sh, int set, unsigned flags, double tol, int frame, cudaStream_t st, const int* stop)
+static void launch_edges(const EvalJob* jobs, int njobs, const EvalShape& sh, int set, unsigned flags, double tol, int frame, cudaStream_t st, const Early& stop)
 {
     const dim3 grid(sh.grid_e + 1, njobs);   // + the service block
     if (sh.dense) {
@@ -545,9 +545,9 @@ static void launch_edges(const EvalJob* jobs, int njobs, const EvalShape& sh, in
 }
 
 // one evaluation of every job: k_edges (or k_setup + k_tiles) then k_corners
-// `stop`: the stop flag of a single-job run (run_state), or null
+// `stop`: what a single-job launch is told as kernel arguments (eval.cuh, Early), all null for a batch
 static void launch_eval(const EvalShape& sh, const EvalJob* jobs, int njobs, int set, unsigned flags, double tol, int frame, cudaStream_t st,
-                        cudaEvent_t mid = nullptr, cudaEvent_t mid0 = nullptr, const int* stop = nullptr)
+                        cudaEvent_t mid = nullptr, cudaEvent_t mid0 = nullptr, const Early& stop = Early{})
 {
     if (sh.path == kPathTiles) {
         k_setup<kTileH><<<dim3(sh.grid_s + 1, njobs), kSetupThreads, 0, st>>>(jobs, set, flags, tol, frame);   // + the service block
@@ -589,13 +589,24 @@ static void issue_direct(const SeqKey& k, cudaStream_t st, cudaEvent_t mid = nul
             if (j > 0) f |= EV_CHECK_PREV;
             if (j == k.len - 1) f |= EV_FINAL;
         }
-        launch_eval(k.shape, k.jobs, k.njobs, (k.first_set + j) & 1, f, k.tol, k.kind == 1 ? j : -1, st, mid, mid0, k.stop);
+        launch_eval(k.shape, k.jobs, k.njobs, (k.first_set + j) & 1, f, k.tol, k.kind == 1 ? j : -1, st, mid, mid0, k.early);
     }
+}
+
+static bool same_early(const Early& a, const Early& b)
+{
+    return a.stop == b.stop && a.edges == b.edges && a.edges_cap == b.edges_cap && a.corner_off == b.corner_off && a.pts == b.pts && a.np_cap == b.np_cap;
+}
+
+// the kernel arguments of a single-job launch of this context (eval.cuh, Early); `in_run`: with the run's stop flag
+static Early early_of(const tpose_cuda_ctx* ctx, bool in_run)
+{
+    return Early{in_run ? ctx->run_state : nullptr, ctx->edges, 3 * ctx->maxT, ctx->corner_off, ctx->pts, ctx->maxP};
 }
 
 static bool same_key(const SeqKey& a, const SeqKey& b)
 {
-    return a.jobs == b.jobs && a.njobs == b.njobs && a.kind == b.kind && a.len == b.len && a.first_set == b.first_set && a.stop == b.stop &&
+    return a.jobs == b.jobs && a.njobs == b.njobs && a.kind == b.kind && a.len == b.len && a.first_set == b.first_set && same_early(a.early, b.early) &&
            a.flags == b.flags && a.tol == b.tol && a.shape.group == b.shape.group && a.shape.grid_e == b.shape.grid_e &&
            a.shape.grid_t == b.shape.grid_t && a.shape.narrow == b.shape.narrow && a.shape.path == b.shape.path &&
            a.shape.grid_s == b.shape.grid_s && a.shape.grid_tiles == b.shape.grid_tiles && a.shape.grid_b == b.shape.grid_b && a.shape.dense == b.shape.dense;
@@ -653,12 +664,12 @@ static int issue_steps(tpose_cuda_ctx* ctx, const EvalJob* jobs, int njobs, cons
     int left = nsteps, set = first_set;
     for (int chunk : {64, 16, 4})
         while (left >= chunk) {
-            int rc = issue_sequence(ctx, SeqKey{jobs, njobs, sh, 0, chunk, set, flags, 0.0});
+            int rc = issue_sequence(ctx, SeqKey{jobs, njobs, sh, 0, chunk, set, flags, 0.0, njobs == 1 ? early_of(ctx, false) : Early{}});
             if (rc) return rc;
             left -= chunk;
         }
     if (left > 0) {
-        int rc = issue_sequence(ctx, SeqKey{jobs, njobs, sh, 0, left, set, flags, 0.0});
+        int rc = issue_sequence(ctx, SeqKey{jobs, njobs, sh, 0, left, set, flags, 0.0, njobs == 1 ? early_of(ctx, false) : Early{}});
         if (rc) return rc;
     }
     return TPOSE_OK;
@@ -715,7 +726,7 @@ static int eval(tpose_cuda_ctx* ctx, int slot, int flavour, int set, unsigned fl
 {
     int rc = sync_job(ctx, slot, flavour);
     if (rc) return rc;
-    rc = issue_sequence(ctx, SeqKey{ctx->job_dev, 1, shape_of(ctx, slot), 0, 1, set, flags, tol});
+    rc = issue_sequence(ctx, SeqKey{ctx->job_dev, 1, shape_of(ctx, slot), 0, 1, set, flags, tol, early_of(ctx, false)});
     ctx->mid_valid = false;      // only tpose_cuda_step brackets its kernels with events
     return rc;
 }
@@ -880,7 +891,7 @@ static int frame_mapped(tpose_cuda_ctx* ctx, int slot, int flavour, const float*
         cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
         if (e == cudaSuccess) {
             if (d_in) k_frame_in<<<(ctx->NP + 255) / 256, 256, 0, ctx->stream>>>((const float2*)d_in, ctx->pts, ctx->NP);
-            launch_eval(sh, ctx->job_dev, 1, set, fused_flags(flavour), 0.0, -1, ctx->stream);
+            launch_eval(sh, ctx->job_dev, 1, set, fused_flags(flavour), 0.0, -1, ctx->stream, nullptr, nullptr, early_of(ctx, false));
             FrameOut f{ctx->ten[set], ctx->cn[set], ctx->ca[set], ctx->pts, (int*)d_ten, (int*)d_cn, (int4*)d_ca, (float2*)d_out, kVariants * ctx->NT, ctx->NP};
             k_frame_out<<<64, 256, 0, ctx->stream>>>(f);
             e = cudaStreamEndCapture(ctx->stream, &graph);
@@ -914,7 +925,7 @@ extern "C" int tpose_cuda_frame(tpose_cuda_ctx* ctx, int slot, int flavour, cons
     if (pts_in_xy && (rc = upload_bytes(ctx, ctx->pts, pts_in_xy, sizeof(float2) * ctx->NP)) != 0) return rc;
     if ((rc = sync_job(ctx, slot, flavour)) != 0) return rc;
     ctx->cur ^= 1;
-    rc = issue_sequence(ctx, SeqKey{ctx->job_dev, 1, shape_of(ctx, slot), 0, 1, ctx->cur, fused_flags(flavour), 0.0});
+    rc = issue_sequence(ctx, SeqKey{ctx->job_dev, 1, shape_of(ctx, slot), 0, 1, ctx->cur, fused_flags(flavour), 0.0, early_of(ctx, false)});
     if (rc) return rc;
     ctx->mid_valid = false;
     const size_t nv = (size_t)kVariants * ctx->NT;
@@ -933,7 +944,7 @@ static int issue_run(tpose_cuda_ctx* lead, const EvalJob* jobs, int njobs, const
                      int flavour, int max_steps, double rel_tol, unsigned extra_flags = 0u)
 {
     return issue_sequence(lead, SeqKey{jobs, njobs, sh, 1, max_steps + 1, first_set, fused_flags(flavour) | EV_HONOUR_STOP | extra_flags, rel_tol,
-                                       njobs == 1 ? lead->run_state : nullptr});
+                                       njobs == 1 ? early_of(lead, true) : Early{}});
 }
 
 extern "C" int tpose_cuda_run(tpose_cuda_ctx* ctx, int slot, int flavour, int max_steps, double rel_tol,

@@ -102,6 +102,17 @@ struct EvalJob {
     unsigned* trig;            // [0] topology trigger accumulator
 };
 
+// What a single-job launch can be told as kernel arguments because it never changes for a context (a captured graph
+// freezes its arguments; everything that does change lives in the job record): the run's stop flag, and the arrays
+// whose first element a thread needs is known from its block and thread index alone.  Those loads are then issued
+// BEFORE the job record is in, so the record's round trip and the first link of the dependent chain (edge ->
+// end points -> table; corner range -> corners -> ...) overlap.  All null for a batch.
+struct Early {
+    const int* stop;           // RS_STOP of a run, or null
+    const int2* edges; int edges_cap;
+    const int* corner_off; const float2* pts; int np_cap;
+};
+
 // shift.cs:16-47 for one vertex; gx, gy are the integer gradient sums
 __device__ __forceinline__ float2 shift_vertex(float2 p, int gxi, int gyi, float ratio, float step)
 {
@@ -362,14 +373,19 @@ __device__ __forceinline__ void walk_edge(EdgeWalk& w, const uint4* __restrict__
 // G lanes per (edge, move) item.  One block of each job's row is the service block.
 template <int G, typename ACC, bool DENSE>
 __global__ void __launch_bounds__(kEdgeThreads, DENSE ? kEdgeBlocksDense : kEdgeBlocksWide)
-k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_tol, int frame, const int* __restrict__ stop_flag)
+k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_tol, int frame, const Early early)
 {
     __shared__ EvalJob J;
     const int tid = threadIdx.x;
     TL(0, 0);
     // a single-job run hands its stop flag over as an argument: the launches behind the stop of a flat chain
     // then cost one load, not a job record and a dependent load
-    if (stop_flag && __ldcg(stop_flag)) return;
+    if (early.stop && __ldcg(early.stop)) return;
+    // ... and its first edge can be on its way before the job record is (single job: block 0 is the service block)
+    int2 ev_early = make_int2(0, 0);
+    const int e_early = (((int)blockIdx.x - 1) * (kEdgeThreads / G) + tid / G) / kEdgeMoves;
+    const bool have_early = early.edges && blockIdx.x > 0 && e_early < early.edges_cap;
+    if (have_early) ev_early = __ldg(early.edges + e_early);
     if (tid < (int)(sizeof(EvalJob) / sizeof(int)))
         reinterpret_cast<int*>(&J)[tid] = reinterpret_cast<const int*>(jobs + blockIdx.y)[tid];
     __syncthreads();
@@ -405,7 +421,7 @@ k_edges(const EvalJob* __restrict__ jobs, int set, unsigned flags, double rel_to
         int sign = 0;
         if (item < nitems) {
             const int e = item / kEdgeMoves, q = item - e * kEdgeMoves;
-            const int2 ev = __ldg(J.edges + e);
+            const int2 ev = (have_early && e == e_early) ? ev_early : __ldg(J.edges + e);
             const float2 pa = J.pts[ev.x], pb = J.pts[ev.y];
 #ifdef TPOSE_TIMELINE
             if (pa.x + pb.x != 12345.0f) TL(0, 2);
@@ -559,12 +575,20 @@ __device__ __forceinline__ int eval_variant(const EvalJob& J, unsigned flags, in
 
 template <typename REC>
 __global__ void __launch_bounds__(kCornerThreads)
-k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame, int base_blocks, const int* __restrict__ stop_flag)
+k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame, int base_blocks, const Early early)
 {
     __shared__ EvalJob J;
     const int tid = threadIdx.x;
     TL(1, 0);
-    if (stop_flag && __ldcg(stop_flag)) return;       // (see k_edges; a block that sees the stop THIS launch raised skips work that is discarded anyway)
+    if (early.stop && __ldcg(early.stop)) return;     // (see k_edges; a block that sees the stop THIS launch raised skips work that is discarded anyway)
+    // the corner range and the position of this warp's first vertex, requested before the job record arrives
+    const int v_early = (int)blockIdx.x * kCornerWarps + (tid >> 5);
+    const bool have_early = early.corner_off && v_early < early.np_cap;
+    int c0_early = 0, c1_early = 0; float2 p_early = make_float2(0.0f, 0.0f);
+    if (have_early) {
+        c0_early = __ldg(early.corner_off + v_early); c1_early = __ldg(early.corner_off + v_early + 1);
+        if ((tid & 31) == 0) p_early = early.pts[v_early];
+    }
     if (tid < (int)(sizeof(EvalJob) / sizeof(int)))
         reinterpret_cast<int*>(&J)[tid] = reinterpret_cast<const int*>(jobs + blockIdx.y)[tid];
     __syncthreads();
@@ -608,9 +632,10 @@ k_corners(const EvalJob* __restrict__ jobs, int set, unsigned flags, int frame, 
     if (flags & EV_FINAL) return;
     const int lane = tid & 31, c_in = lane >> 2, s = lane & 3;
     for (int v = (int)blockIdx.x * kCornerWarps + (tid >> 5); v < J.NP; v += nvb * kCornerWarps) {
-        const int c0 = __ldg(J.corner_off + v), c1 = __ldg(J.corner_off + v + 1);
+        const bool pre = have_early && v == v_early;
+        const int c0 = pre ? c0_early : __ldg(J.corner_off + v), c1 = pre ? c1_early : __ldg(J.corner_off + v + 1);
         float2 p = make_float2(0.0f, 0.0f);
-        if (lane == 0) p = J.pts[v];
+        if (lane == 0) p = pre ? p_early : J.pts[v];
         unsigned gx = 0u, gy = 0u;
         for (int cb = c0; cb < c1; cb += 8) {
             const int c = cb + c_in;
