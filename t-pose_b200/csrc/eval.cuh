@@ -195,15 +195,16 @@ __device__ int watch_triangle(const EvalJob& J, int t)
 // geterr (source/triangulation.hpp:653-674): float32 running sum of the base energies in index order.  Order
 // matters (float addition is not associative), so the additions are one dependent chain -- but nothing else has
 // to be serial: one WARP runs it.  Every lane loads its share of the next 256 energies (coalesced, converted to
-// float, issued one round ahead of their use), and all lanes add the same 256 values in index order, fetching
-// each from the lane that holds it with a shuffle.  The chain then costs one FADD latency per element (~2 ns)
+// float, issued one round ahead of their use) and parks them in shared memory; all lanes then add the same 256
+// values in index order, four per broadcast 16-byte load.  The chain then costs one FADD latency per element (~2 ns)
 // instead of a dependent global load every few elements (one thread: 28 us at 3 000 triangles, measured --
 // three times the rest of the step, and k_edges cannot end before its service block does).
 // Elements past nt are +0.0f: s + 0 = s exactly (s is never -0: it starts at +0 and a zero sum rounds to +0).
 __device__ void geterr_warp(const int* __restrict__ ten_base, int nt, float* state, double rel_tol, int lane)
 {
     constexpr int K = 8;                       // registers per lane and round: 32 * K energies per round
-    float cur[K], nxt[K];
+    __shared__ __align__(16) float s_round[2][32 * K];      // the round being added | the next one
+    float nxt[K];
     auto load = [&](int base, float (&r)[K]) {
 #pragma unroll
         for (int j = 0; j < K; j++) {
@@ -211,16 +212,28 @@ __device__ void geterr_warp(const int* __restrict__ ten_base, int nt, float* sta
             r[j] = i < nt ? (float)__ldcg(ten_base + i) : 0.0f;
         }
     };
+    auto stage = [&](int buf, const float (&r)[K]) {
+#pragma unroll
+        for (int j = 0; j < K; j++) s_round[buf][32 * j + lane] = r[j];
+    };
     float newerr = 0.0f;
-    load(0, cur);
-    for (int base = 0; base < nt; base += 32 * K) {
-        if (base + 32 * K < nt) load(base + 32 * K, nxt);
-#pragma unroll
-        for (int j = 0; j < K; j++)
-#pragma unroll
-            for (int l = 0; l < 32; l++) newerr = __fadd_rn(newerr, __shfl_sync(0xffffffffu, cur[j], l));
-#pragma unroll
-        for (int j = 0; j < K; j++) cur[j] = nxt[j];
+    load(0, nxt);
+    stage(0, nxt);
+    __syncwarp();
+    int buf = 0;
+    for (int base = 0; base < nt; base += 32 * K, buf ^= 1) {
+        const bool more = base + 32 * K < nt;
+        if (more) load(base + 32 * K, nxt);                  // in flight while this round is added
+        // every lane adds the same 256 values in index order, four per broadcast 16-byte load: the chain is the FADDs
+        const float4* q = reinterpret_cast<const float4*>(s_round[buf]);
+#pragma unroll 16
+        for (int i = 0; i < 8 * K; i++) {
+            const float4 v = q[i];
+            newerr = __fadd_rn(newerr, v.x); newerr = __fadd_rn(newerr, v.y);
+            newerr = __fadd_rn(newerr, v.z); newerr = __fadd_rn(newerr, v.w);
+        }
+        if (more) stage(buf ^ 1, nxt);
+        __syncwarp();
     }
     if (lane != 0) return;
     const float tot = state[0];
