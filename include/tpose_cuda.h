@@ -300,6 +300,15 @@ int tpose_cuda_triangulate(int device, const float *F9, const float *K9, const f
  * (row-major float[12]).  X4_out is NOT divided by w; sign: largest component positive. */
 int tpose_cuda_hdlt(int device, const float *PA12, const float *PB12, const float *A_xy, const float *B_xy,
                     int n, float *X4_out);
+/* geterr (source/triangulation.hpp:653-674) over `n` int32 energies on the device: newerr = their float32 sum in index
+ * order, relerr = |(*toterr_inout - newerr) / *toterr_inout|, *toterr_inout = newerr, *below_tol_out = relerr < rel_tol
+ * (float against a double literal, as `geterr(&tr) < 1E-4` compares).  This is the routine every frame of
+ * tpose_cuda_run ends with (csrc/eval.cuh), exposed on its own.  route: -1 as a run would choose for this n,
+ * 0 the literal chain of additions by one warp, 1 the block-parallel routine (geterr_block) -- same bits.
+ * relerr_out / below_tol_out may be NULL.  Errors: tpose_cuda_mview_last_error(). */
+int tpose_cuda_geterr(int device, const int32_t *energies, int n, float *toterr_inout, float *relerr_out,
+                      int *below_tol_out, double rel_tol, int route);
+
 /* triangulation::warp / reversewarp (source/triangulation.hpp:465-520): every point of pts_xy that
  * is not on the domain boundary (|x| >= ratio or |y| >= 1) is located in the first triangle, in
  * index order, of the embedding from_xy that strictly contains it, and replaced by the point with

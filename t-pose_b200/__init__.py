@@ -43,7 +43,7 @@ EXPORTS = [
     "tpose_cuda_retrieve", "tpose_cuda_retrieve_base", "tpose_cuda_retrieve_gradient",
     "tpose_cuda_raster_ids", "tpose_cuda_render", "tpose_cuda_render_wire", "tpose_cuda_last_elapsed_ms", "tpose_cuda_last_kernel_ms", "tpose_cuda_last_setup_ms", "tpose_cuda_kernel_path", "tpose_cuda_set_kernel_timing", "tpose_cuda_set_step_scale", "tpose_cuda_sync",
     "tpose_cuda_launch_count", "tpose_cuda_host_alloc", "tpose_cuda_host_free", "tpose_cuda_flush_l2",
-    "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_rgbd_planefit", "tpose_cuda_select_matches", "tpose_cuda_carry", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
+    "tpose_cuda_f8point", "tpose_cuda_fsampson", "tpose_cuda_rgbd_planefit", "tpose_cuda_select_matches", "tpose_cuda_carry", "tpose_cuda_geterr", "tpose_cuda_triangulate", "tpose_cuda_hdlt", "tpose_cuda_mview_last_error",
     "tpose_cuda_mview_last_ms",
     "tpose_cuda_watch", "tpose_cuda_watch_mask", "tpose_cuda_set_history", "tpose_cuda_eval_list", "tpose_cuda_history_frame", "tpose_cuda_history_restore_gradient", "tpose_cuda_read", "tpose_cuda_write", "tpose_cuda_batch_step", "tpose_cuda_batch_run",
 ]
@@ -395,6 +395,16 @@ def hdlt(PA, PB, A, B, device=0):
     X = np.zeros((A.shape[0], 4), np.float32)
     _mview_ck(lib().tpose_cuda_hdlt(device, _ptr(PA), _ptr(PB), _ptr(A), _ptr(B), A.shape[0], _ptr(X)), "hdlt")
     return X
+
+
+def geterr(energies, toterr=1.0, rel_tol=1e-4, device=0, route=-1):
+    """geterr over an int32 array on the device: (newerr, relerr, relerr < rel_tol).  route: -1 as a run chooses,
+    0 the plain chain, 1 the block-parallel routine."""
+    e = np.ascontiguousarray(energies, np.int32)
+    tot, rel, below = C.c_float(toterr), C.c_float(), C.c_int()
+    _mview_ck(lib().tpose_cuda_geterr(device, _ptr(e) if e.size else _ptr(np.zeros(1, np.int32)), int(e.size), C.byref(tot), C.byref(rel),
+                                      C.byref(below), C.c_double(rel_tol), C.c_int(route)), "geterr")
+    return np.float32(tot.value), np.float32(rel.value), bool(below.value)
 
 
 def carry(tri, frm, to, pts, ratio, device=0):

@@ -1775,6 +1775,33 @@ extern "C" int tpose_cuda_select_matches(int device, const float* originA_xy, co
     return TPOSE_OK;
 }
 
+// geterr (source/triangulation.hpp:653-674) over an array of energies: the kernel-side routine of the runs on its own
+extern "C" int tpose_cuda_geterr(int device, const int32_t* energies, int n, float* toterr_inout, float* relerr_out, int* below_tol_out, double rel_tol,
+                                 int route)
+{
+    if (!energies || n < 0 || !toterr_inout) return mview_fail(TPOSE_ERR_ARG, "geterr: bad arguments");
+    MviewWs* ws = nullptr;
+    int rc = mview_workspace(device, padded(sizeof(int) * (size_t)(n > 0 ? n : 1)) + padded(4 * sizeof(float)) + 1024, &ws);
+    if (rc) return rc;
+    int* dE = carve<int>(ws, n > 0 ? n : 1); float* dS = carve<float>(ws, 4);
+    cudaStream_t st = ws->stream;
+    const float st4[4] = {*toterr_inout, 0.0f, 0.0f, 0.0f};
+    float out4[4];
+    if (n > 0) MCK(cudaMemcpyAsync(dE, energies, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dS, st4, sizeof st4, cudaMemcpyHostToDevice, st));
+    MCK(cudaEventRecord(ws->e0, st));
+    k_geterr<<<1, kGeterrThreads, 0, st>>>(dE, n, dS, rel_tol, route < 0 ? -1 : (route ? 1 : 0));
+    MCK(cudaGetLastError());
+    MCK(cudaEventRecord(ws->e1, st));
+    MCK(cudaMemcpyAsync(out4, dS, sizeof out4, cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&g_mview_ms, ws->e0, ws->e1);         // tpose_cuda_mview_last_ms: the kernel alone
+    *toterr_inout = out4[0];
+    if (relerr_out) *relerr_out = out4[1];
+    if (below_tol_out) *below_tol_out = out4[3] != 0.0f;
+    return TPOSE_OK;
+}
+
 extern "C" int tpose_cuda_carry(int device, const int32_t* tri_xyzw, int nt, const float* from_xy, const float* to_xy, int nv,
                                 float* pts_xy, int npts, float ratio)
 {

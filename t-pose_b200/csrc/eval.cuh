@@ -193,13 +193,47 @@ __device__ int watch_triangle(const EvalJob& J, int t)
 }
 
 // geterr (source/triangulation.hpp:653-674): float32 running sum of the base energies in index order.  Order
-// matters (float addition is not associative), so the additions are one dependent chain -- but nothing else has
-// to be serial: one WARP runs it.  Every lane loads its share of the next 256 energies (coalesced, converted to
-// float, issued one round ahead of their use) and parks them in shared memory; all lanes then add the same 256
-// values in index order, four per broadcast 16-byte load.  The chain then costs one FADD latency per element (~2 ns)
-// instead of a dependent global load every few elements (one thread: 28 us at 3 000 triangles, measured --
-// three times the rest of the step, and k_edges cannot end before its service block does).
-// Elements past nt are +0.0f: s + 0 = s exactly (s is never -0: it starts at +0 and a zero sum rounds to +0).
+// matters (float addition is not associative), so taken literally it is one dependent chain of NT additions: 4 ns
+// each on this part however the addends are fed (one thread chasing global loads: 28 us at 3 000 triangles; one warp
+// with the round staged in shared memory: 12 us, 41 us at 10 000) -- and k_edges cannot end before its service
+// block does.  What is serial in it is much less than that:
+//
+// The sum by the whole service block, exactly, in a few microseconds whatever NT is.  With non-negative addends the running sum s never decreases.  While s < 2^24 every addition is exact.  Inside a
+// binade [2^e, 2^(e+1)), e >= 24, s is a multiple of U = 2^(e-23) and adding a = q U + r (0 <= r < U) gives
+// s + U (q + c): c = 0 if r < U/2, 1 if r > U/2, and on an exact tie (r = U/2, round to even) c = parity of (s/U + q).
+// So as long as the sum stays inside one binade, a run of additions is a function of ONE bit of s -- the parity of
+// s/U, which is the last mantissa bit of the float -- that returns an increment in units of U: (inc_0, inc_1).  Two
+// such runs compose: inc_p = A.inc_p + B.inc_[(p + A.inc_p) & 1].
+//   1. every thread takes a contiguous chunk, sums it exactly (int64) and a block scan gives the exact prefix P in
+//      front of the chunk; the binade of P is the thread's GUESS for the binade the float sum is in there;
+//   2. the thread folds its chunk into (inc_0, inc_1) under that guess; groups of 8 threads with the same guess are
+//      folded once more;
+//   3. one thread walks the 32 groups with the real float sum: a summary is used only if the sum is in the guessed
+//      binade before it and still in it after it (monotone: then it was there all the way, and the increment is
+//      exact) -- otherwise the group's 8 thread summaries are tried the same way, and a chunk whose summary fails
+//      (it straddles a power of two, holds a negative energy, ...) is added the plain way, one FADD per element.
+// Nothing is assumed about how well the guess fits: a wrong guess costs time, never a bit.  About one group in two
+// and seven chunks fall back on a 1.5e9 total (seven binades above 2^24).  Model and randomized check against the
+// serial float32 loop: tests/test_geterr_cpu.py; on the device: tests/test_step_gpu.py.
+constexpr int kGeterrThreads = 256, kGeterrGroup = 8;
+constexpr int kGeterrBlockMin = 1792;      // below this many energies the plain chain of one warp is quicker (measured:
+                                           // chain 8.1 us + 4.4 ns per element, block routine ~12 us + 0.75 ns, kernel alone)
+
+// the verdict of geterr from the new sum
+__device__ __forceinline__ void geterr_finish(float newerr, float* state, double rel_tol)
+{
+    const float tot = state[0];
+    const float rel = __fdiv_rn(__fsub_rn(tot, newerr), tot);
+    state[0] = newerr;
+    state[1] = fabsf(rel);
+    state[2] = newerr;
+    // the reference compares the float against a double literal (`geterr(&tr) < 1E-4`)
+    state[3] = ((double)fabsf(rel) < rel_tol) ? 1.0f : 0.0f;
+}
+
+// The literal chain by one warp: every lane loads its share of the next 256 energies (coalesced, converted to float,
+// issued one round ahead of their use) and parks them in shared memory; all lanes then add the same 256 values in
+// index order, four per broadcast 16-byte load.  Elements past nt are +0.0f: s + 0 = s exactly (s is never -0).
 __device__ void geterr_warp(const int* __restrict__ ten_base, int nt, float* state, double rel_tol, int lane)
 {
     constexpr int K = 8;                       // registers per lane and round: 32 * K energies per round
@@ -224,7 +258,6 @@ __device__ void geterr_warp(const int* __restrict__ ten_base, int nt, float* sta
     for (int base = 0; base < nt; base += 32 * K, buf ^= 1) {
         const bool more = base + 32 * K < nt;
         if (more) load(base + 32 * K, nxt);                  // in flight while this round is added
-        // every lane adds the same 256 values in index order, four per broadcast 16-byte load: the chain is the FADDs
         const float4* q = reinterpret_cast<const float4*>(s_round[buf]);
 #pragma unroll 16
         for (int i = 0; i < 8 * K; i++) {
@@ -235,19 +268,130 @@ __device__ void geterr_warp(const int* __restrict__ ten_base, int nt, float* sta
         if (more) stage(buf ^ 1, nxt);
         __syncwarp();
     }
-    if (lane != 0) return;
-    const float tot = state[0];
-    const float rel = __fdiv_rn(__fsub_rn(tot, newerr), tot);
-    state[0] = newerr;
-    state[1] = fabsf(rel);
-    state[2] = newerr;
-    // the reference compares the float against a double literal (`geterr(&tr) < 1E-4`)
-    state[3] = ((double)fabsf(rel) < rel_tol) ? 1.0f : 0.0f;
+    if (lane == 0) geterr_finish(newerr, state, rel_tol);
+}
+
+// a summary as the walk wants it: the two increments as floats (exact: < 2^24 units of a power of two), the binade's
+// lower bound (0 below 2^24, where every sum is exact) and the bound the sum must stay under; lim = 0: no summary
+__device__ __forceinline__ float4 geterr_pack(unsigned long long inc0, unsigned long long inc1, int e)
+{
+    if (e < 0 || inc0 >= (1ull << 24) || inc1 >= (1ull << 24)) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const int sh = max(e - 23, 0);
+    const float unit = __uint_as_float((unsigned)(127 + sh) << 23);
+    return make_float4(__fmul_rn((float)(unsigned)inc0, unit), __fmul_rn((float)(unsigned)inc1, unit),
+                       sh > 0 ? __uint_as_float((unsigned)(127 + e) << 23) : 0.0f, __uint_as_float((unsigned)(127 + max(e, 23) + 1) << 23));
+}
+// s + increment if s is in the summary's binade before and after
+__device__ __forceinline__ bool geterr_try(float& s, const float4 S)
+{
+    const float out = __fadd_rn(s, (__float_as_uint(s) & 1u) ? S.y : S.x);
+    if (!(s >= S.z) || !(out < S.w)) return false;
+    s = out;
+    return true;
+}
+
+__device__ void geterr_block(const int* __restrict__ ten_base, int nt, float* state, double rel_tol, int tid, int nthreads)
+{
+    __shared__ float4 s_sum[kGeterrThreads], s_grp[kGeterrThreads / kGeterrGroup];
+    __shared__ unsigned s_inc0[kGeterrThreads], s_inc1[kGeterrThreads];
+    __shared__ int s_e[kGeterrThreads];                        // binade guess; -1: no summary; -2: empty chunk
+    __shared__ unsigned long long s_wsum[kGeterrThreads / 32];
+    const int T = nthreads;                                    // <= kGeterrThreads (both callers launch 256)
+    const int C = 4 * ((nt + 4 * T - 1) / (4 * T));            // chunk length, a multiple of 4: 16-byte loads
+    const int lane = tid & 31, wid = tid >> 5;
+    const int i0 = min(tid * C, nt), i1 = min(i0 + C, nt);
+    // four energies as the exact integer values of their floats; past the end: 0
+    auto load4 = [&](int i, unsigned long long (&a)[4], bool& neg) {
+        int4 v = make_int4(0, 0, 0, 0);
+        if (i + 4 <= nt) v = __ldg(reinterpret_cast<const int4*>(ten_base + i));
+        else { if (i < nt) v.x = __ldg(ten_base + i); if (i + 1 < nt) v.y = __ldg(ten_base + i + 1); if (i + 2 < nt) v.z = __ldg(ten_base + i + 2); }
+        neg |= (v.x | v.y | v.z | v.w) < 0;
+        a[0] = (unsigned long long)(long long)(float)max(v.x, 0); a[1] = (unsigned long long)(long long)(float)max(v.y, 0);
+        a[2] = (unsigned long long)(long long)(float)max(v.z, 0); a[3] = (unsigned long long)(long long)(float)max(v.w, 0);
+    };
+    // 1. exact chunk sum of the float values of the energies, and the exact prefix in front of the chunk
+    unsigned long long sum = 0ull; bool neg = false;
+    for (int i = i0; i < i1; i += 4) {
+        unsigned long long a[4];
+        load4(i, a, neg);
+        sum += (a[0] + a[1]) + (a[2] + a[3]);
+    }
+    unsigned long long incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    unsigned long long P0 = incl - sum;
+    for (int w = 0; w < wid; w++) P0 += s_wsum[w];
+    // 2. the chunk as a function of the parity of s / U, under the binade of P0
+    {
+        int e = -2;
+        unsigned long long t0 = 0ull, t1 = 0ull;              // increments in units of U for entry parity 0 / 1
+        if (i0 < i1) {
+            e = P0 ? 63 - __clzll((long long)P0) : 0;
+            const int sh = max(e - 23, 0);
+            const unsigned long long mask = (1ull << sh) - 1ull, half = (1ull << sh) >> 1;
+            bool dummy = false;
+            for (int i = i0; i < i1; i += 4) {
+                unsigned long long a[4];
+                load4(i, a, dummy);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const unsigned long long q = a[k] >> sh, r = a[k] & mask;
+                    const unsigned long long tie = (sh > 0 && r == half) ? 1ull : 0ull, up = (sh > 0 && r > half) ? 1ull : 0ull;
+                    t0 += q + up + (tie & (q + t0));           // parity before the add = (entry parity + increments so far) & 1
+                    t1 += q + up + (tie & (q + t1 + 1ull));
+                }
+            }
+            if (neg || t0 >= (1ull << 24) || t1 >= (1ull << 24)) e = -1;
+        }
+        s_inc0[tid] = (unsigned)t0; s_inc1[tid] = (unsigned)t1; s_e[tid] = e;
+        s_sum[tid] = geterr_pack(t0, t1, e);
+    }
+    __syncthreads();
+    // groups of kGeterrGroup chunks with one common guess
+    if (tid % kGeterrGroup == 0) {
+        int ge = -2; unsigned long long g0 = 0ull, g1 = 0ull;
+        for (int t = tid; t < min(tid + kGeterrGroup, T); t++) {
+            const int e = s_e[t];
+            if (e == -2) continue;
+            if (e < 0 || ge == -1 || (ge >= 0 && e != ge)) { ge = -1; continue; }
+            ge = e;
+            g0 += (g0 & 1ull) ? s_inc1[t] : s_inc0[t];                 // parity in front of chunk t = (entry parity + increments so far) & 1
+            g1 += ((g1 + 1ull) & 1ull) ? s_inc1[t] : s_inc0[t];
+        }
+        s_grp[tid / kGeterrGroup] = ge == -2 ? make_float4(0.0f, 0.0f, 0.0f, 1e38f) : geterr_pack(g0, g1, ge);   // (all empty: + 0, always fine)
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    // 3. the real sum walks the summaries
+    float newerr = 0.0f;
+    for (int g = 0; g * kGeterrGroup < T; g++) {
+        if (geterr_try(newerr, s_grp[g])) continue;
+        for (int t = g * kGeterrGroup; t < min((g + 1) * kGeterrGroup, T); t++) {
+            if (s_e[t] == -2 || geterr_try(newerr, s_sum[t])) continue;
+            const int j0 = min(t * C, nt), j1 = min(j0 + C, nt);
+            for (int i = j0; i < j1; i++) newerr = __fadd_rn(newerr, (float)__ldg(ten_base + i));
+        }
+    }
+    geterr_finish(newerr, state, rel_tol);
+}
+
+// geterr over an array of energies on its own (tpose_cuda_geterr): state = err_state
+// (`by_block`: 1 the block routine, 0 the warp chain, -1 whichever a run would take for this n)
+__global__ void __launch_bounds__(kGeterrThreads) k_geterr(const int* __restrict__ energies, int n, float* state, double rel_tol, int by_block)
+{
+    if (by_block < 0) by_block = n >= kGeterrBlockMin;
+    if (by_block) geterr_block(energies, n, state, rel_tol, threadIdx.x, kGeterrThreads);
+    else if (threadIdx.x < 32) geterr_warp(energies, n, state, rel_tol, threadIdx.x);
 }
 
 // ---- the service block (shared by k_edges and k_setup) ---------------------------------------------
 // Pulls the static index arrays k_corners is about to chase through into L2, then runs the previous
-// frame's host-side checks: geterr (the last warp) and the topology watch (the others).
+// frame's host-side checks: geterr (geterr_block) and the topology watch.
 __device__ void service_block(EvalJob& J, int set, unsigned flags, double rel_tol, int frame, int tid, int nthreads, bool single_job)
 {
     if (!(flags & EV_FINAL) && single_job) {
@@ -267,12 +411,16 @@ __device__ void service_block(EvalJob& J, int set, unsigned flags, double rel_to
     unsigned* const mask = hist ? J.hist_mask + (size_t)(frame - 1) * words : J.wmask;
     if (J.wtri || hist) for (int w = tid; w < words; w += nthreads) mask[w] = 0u;   // (no watch topology: an empty mask)
     __syncthreads();
-    if (tid >= nthreads - 32) {               // the last warp: geterr
-        geterr_warp(J.ten[set ^ 1], J.NT, J.err_state, rel_tol, tid & 31);
-        if (hist && tid == nthreads - 32) J.hist_err[frame - 1] = J.err_state[0];
-    } else if (J.wtri) {
+    // geterr.  Small meshes: the last warp runs the plain chain while the others watch.  Larger ones: the parallel part
+    // by everybody, then thread 0 walks the summaries while the others start on the watch.
+    const bool by_block = J.NT >= kGeterrBlockMin;
+    if (by_block) geterr_block(J.ten[set ^ 1], J.NT, J.err_state, rel_tol, tid, nthreads);
+    else if (tid >= nthreads - 32) geterr_warp(J.ten[set ^ 1], J.NT, J.err_state, rel_tol, tid & 31);
+    if (hist && tid == (by_block ? 0 : nthreads - 32)) J.hist_err[frame - 1] = J.err_state[0];
+    if (J.wtri && (by_block || tid < nthreads - 32)) {
+        const int watchers = by_block ? nthreads : nthreads - 32;
         bool hit = false;
-        for (int t = tid; t < J.NT; t += nthreads - 32) {
+        for (int t = tid; t < J.NT; t += watchers) {
             const int code = watch_triangle(J, t);
             if (code) atomicOr(&mask[t >> 5], 1u << (t & 31));
             hit |= (flags & EV_HISTORY) ? code == 2 : code != 0;

@@ -527,3 +527,22 @@ def test_run_results_reach_the_host_without_copy_engine_operations(cuda_pkg, syn
         assert done == 5
         assert c.launch_count() - n0 == per_eval * 6 + 1
     c.close()
+
+
+def test_geterr_on_the_device_equals_the_serial_float_sum(cuda_pkg):
+    """tpose_cuda_geterr = geterr_block (csrc/eval.cuh), the routine every frame of a run ends with: the float32 sum of
+    the energies in index order (source/triangulation.hpp:653-674), computed from per-chunk summaries that depend on
+    one bit of the running sum.  Bit-equal to the literal serial loop on plain, adversarial (ties in every binade,
+    powers of two, zeros, negative energies, int -> float rounding of the addends) and large inputs."""
+    from geterr_model import serial_f32, cases
+    rng = np.random.default_rng(23)
+    inputs = list(cases(rng, 150)) + [np.abs(rng.normal(1.5e9 / n, 0.5e9 / n, n)).astype(np.int32) for n in (150, 3000, 10000, 40000)]
+    inputs += [np.zeros(0, np.int32), np.array([7], np.int32), np.array([2 ** 24, 1, 1, 1], np.int32), np.full(5000, 1, np.int32)]
+    for x in inputs:
+        want = serial_f32(x)
+        tot = np.float32(rng.uniform(1.0, 3e9))
+        wrel = np.float32(abs(np.float32((tot - want) / tot)))
+        for route in (1, 0, -1):                      # the block routine, the plain chain, what a run picks
+            got, rel, below = cuda_pkg.geterr(x, toterr=float(tot), rel_tol=1e-4, route=route)
+            assert got.view(np.uint32) == want.view(np.uint32), (len(x), route, got, want)
+            assert rel.view(np.uint32) == wrel.view(np.uint32) and below == (float(wrel) < 1e-4)
