@@ -284,7 +284,8 @@ __device__ __forceinline__ float4 geterr_pack(unsigned long long inc0, unsigned 
 // s + increment if s is in the summary's binade before and after
 __device__ __forceinline__ bool geterr_try(float& s, const float4 S)
 {
-    const float out = __fadd_rn(s, (__float_as_uint(s) & 1u) ? S.y : S.x);
+    const float o0 = __fadd_rn(s, S.x), o1 = __fadd_rn(s, S.y);       // (both, so that the parity test is off the chain)
+    const float out = (__float_as_uint(s) & 1u) ? o1 : o0;
     if (!(s >= S.z) || !(out < S.w)) return false;
     s = out;
     return true;
@@ -368,14 +369,25 @@ __device__ void geterr_block(const int* __restrict__ ten_base, int nt, float* st
     __syncthreads();
     if (tid != 0) return;
     // 3. the real sum walks the summaries
+    // (the next summary is fetched before the current one is tried: the walk is one dependent chain through newerr)
     float newerr = 0.0f;
-    for (int g = 0; g * kGeterrGroup < T; g++) {
-        if (geterr_try(newerr, s_grp[g])) continue;
-        for (int t = g * kGeterrGroup; t < min((g + 1) * kGeterrGroup, T); t++) {
-            if (s_e[t] == -2 || geterr_try(newerr, s_sum[t])) continue;
-            const int j0 = min(t * C, nt), j1 = min(j0 + C, nt);
-            for (int i = j0; i < j1; i++) newerr = __fadd_rn(newerr, (float)__ldg(ten_base + i));
+    const int ng = (T + kGeterrGroup - 1) / kGeterrGroup;
+    float4 G = s_grp[0];
+    for (int g = 0; g < ng; g++) {
+        const float4 Gnext = s_grp[min(g + 1, ng - 1)];
+        if (!geterr_try(newerr, G)) {
+            const int t1 = min((g + 1) * kGeterrGroup, T);
+            float4 S = s_sum[g * kGeterrGroup];
+            for (int t = g * kGeterrGroup; t < t1; t++) {
+                const float4 Snext = s_sum[min(t + 1, t1 - 1)];
+                if (s_e[t] != -2 && !geterr_try(newerr, S)) {
+                    const int j0 = min(t * C, nt), j1 = min(j0 + C, nt);
+                    for (int i = j0; i < j1; i++) newerr = __fadd_rn(newerr, (float)__ldg(ten_base + i));
+                }
+                S = Snext;
+            }
         }
+        G = Gnext;
     }
     geterr_finish(newerr, state, rel_tol);
 }
