@@ -8,18 +8,19 @@
 //            first end point moved by (+dp,0),(-dp,0),(0,+dp),(0,-dp), q = 5..8 its second one.
 //            An interior edge is shared by two triangles and its nine integrals serve both (with
 //            opposite sign), so the table is walked once per edge, not once per triangle side.
-//            Results go to a 48-byte record per item.
+//            Results go to a 32-byte record per item (48 where the colour sums need 64 bits).
 //   k_corners one thread per (triangle, variant k): three records -> moments -> cn/ca/ten.  The
 //            moved variants are grouped by the vertex they move (one warp per vertex), so
 //            gradient.cs becomes a warp reduction and shift.cs follows in the same warp.
 //
 // A step can also carry the host-side checks of the PREVIOUS frame (EV_CHECK_PREV), so that a run
 // of frames needs no host round trip and no serial check between frames:
-//   * geterr (source/triangulation.hpp:653-674) over the previous frame's base energies, by one
-//     warp of k_edges' service block (one in-order chain of float32 additions), overlapped with the edge walks;
+//   * geterr (source/triangulation.hpp:653-674) over the previous frame's base energies, by k_edges' service
+//     block -- the in-order float32 sum, as a plain chain (geterr_warp) or block-parallel (geterr_block) --
+//     overlapped with the edge walks;
 //   * a conservative test of the per-frame topology edits of software/triangulate/main.cpp:316-346
 //     (prune / >0.8*pi flip / short-edge collapse) on the host's ("watch") topology at the current
-//     points, by the other threads of the service block.
+//     points, by the service block as well.
 // If either fires, k_corners does NOT apply this step's shift and raises the stop
 // flag: points, and the other buffer set, are then exactly what the reference holds after the
 // frame whose checks fired.  The evaluation done by this step is speculative and discarded.
