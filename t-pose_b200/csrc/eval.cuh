@@ -216,7 +216,9 @@ __device__ int watch_triangle(const EvalJob& J, int t)
 // Nothing is assumed about how well the guess fits: a wrong guess costs time, never a bit.  About one group in two
 // and seven chunks fall back on a 1.5e9 total (seven binades above 2^24).  Model and randomized check against the
 // serial float32 loop: tests/test_geterr_cpu.py; on the device: tests/test_step_gpu.py.
-constexpr int kGeterrThreads = 256, kGeterrGroup = 8;
+constexpr int kGeterrThreads = 256, kGeterrGroup = 8;         // (a group sits inside one warp: it is folded with shuffles)
+// scratch of either routine: 256 chunk summaries + 32 group summaries + 8 warp sums | two rounds of 256 floats
+constexpr int kGeterrSmemBytes = kGeterrThreads * 16 + (kGeterrThreads / kGeterrGroup) * 16 + (kGeterrThreads / 32) * 8;
 constexpr int kGeterrBlockMin = 1792;      // below this many energies the plain chain of one warp is quicker (measured:
                                            // chain 8.1 us + 4.4 ns per element, block routine ~12 us + 0.75 ns, kernel alone)
 
@@ -235,10 +237,10 @@ __device__ __forceinline__ void geterr_finish(float newerr, float* state, double
 // The literal chain by one warp: every lane loads its share of the next 256 energies (coalesced, converted to float,
 // issued one round ahead of their use) and parks them in shared memory; all lanes then add the same 256 values in
 // index order, four per broadcast 16-byte load.  Elements past nt are +0.0f: s + 0 = s exactly (s is never -0).
-__device__ void geterr_warp(const int* __restrict__ ten_base, int nt, float* state, double rel_tol, int lane)
+__device__ void geterr_warp(const int* __restrict__ ten_base, int nt, float* state, double rel_tol, int lane, unsigned char* scratch)
 {
     constexpr int K = 8;                       // registers per lane and round: 32 * K energies per round
-    __shared__ __align__(16) float s_round[2][32 * K];      // the round being added | the next one
+    float (*s_round)[32 * K] = reinterpret_cast<float (*)[32 * K]>(scratch);     // [2]: the round being added | the next one
     float nxt[K];
     auto load = [&](int base, float (&r)[K]) {
 #pragma unroll
@@ -292,12 +294,11 @@ __device__ __forceinline__ bool geterr_try(float& s, const float4 S)
     return true;
 }
 
-__device__ void geterr_block(const int* __restrict__ ten_base, int nt, float* state, double rel_tol, int tid, int nthreads)
+__device__ void geterr_block(const int* __restrict__ ten_base, int nt, float* state, double rel_tol, int tid, int nthreads, unsigned char* scratch)
 {
-    __shared__ float4 s_sum[kGeterrThreads], s_grp[kGeterrThreads / kGeterrGroup];
-    __shared__ unsigned s_inc0[kGeterrThreads], s_inc1[kGeterrThreads];
-    __shared__ int s_e[kGeterrThreads];                        // binade guess; -1: no summary; -2: empty chunk
-    __shared__ unsigned long long s_wsum[kGeterrThreads / 32];
+    float4* const s_sum = reinterpret_cast<float4*>(scratch);                              // [kGeterrThreads]
+    float4* const s_grp = s_sum + kGeterrThreads;                                           // [kGeterrThreads / kGeterrGroup]
+    unsigned long long* const s_wsum = reinterpret_cast<unsigned long long*>(s_grp + kGeterrThreads / kGeterrGroup);   // [kGeterrThreads / 32]
     const int T = nthreads;                                    // <= kGeterrThreads (both callers launch 256)
     const int C = 4 * ((nt + 4 * T - 1) / (4 * T));            // chunk length, a multiple of 4: 16-byte loads
     const int lane = tid & 31, wid = tid >> 5;
@@ -328,10 +329,10 @@ __device__ void geterr_block(const int* __restrict__ ten_base, int nt, float* st
     __syncthreads();
     unsigned long long P0 = incl - sum;
     for (int w = 0; w < wid; w++) P0 += s_wsum[w];
-    // 2. the chunk as a function of the parity of s / U, under the binade of P0
+    // 2. the chunk as a function of the parity of s / U, under the binade of P0 (e: the guess; -1: no summary; -2: empty chunk)
+    int e = -2;
+    unsigned long long t0 = 0ull, t1 = 0ull;                  // increments in units of U for entry parity 0 / 1
     {
-        int e = -2;
-        unsigned long long t0 = 0ull, t1 = 0ull;              // increments in units of U for entry parity 0 / 1
         if (i0 < i1) {
             e = P0 ? 63 - __clzll((long long)P0) : 0;
             const int sh = max(e - 23, 0);
@@ -350,22 +351,24 @@ __device__ void geterr_block(const int* __restrict__ ten_base, int nt, float* st
             }
             if (neg || t0 >= (1ull << 24) || t1 >= (1ull << 24)) e = -1;
         }
-        s_inc0[tid] = (unsigned)t0; s_inc1[tid] = (unsigned)t1; s_e[tid] = e;
-        s_sum[tid] = geterr_pack(t0, t1, e);
+        s_sum[tid] = e == -2 ? make_float4(0.0f, 0.0f, 0.0f, 1e38f) : geterr_pack(t0, t1, e);    // (empty: + 0, always fine)
     }
-    __syncthreads();
-    // groups of kGeterrGroup chunks with one common guess
-    if (tid % kGeterrGroup == 0) {
+    // groups of kGeterrGroup chunks with one common guess: every lane folds its group's eight summaries in order
+    {
+        const int first = lane & ~(kGeterrGroup - 1);
         int ge = -2; unsigned long long g0 = 0ull, g1 = 0ull;
-        for (int t = tid; t < min(tid + kGeterrGroup, T); t++) {
-            const int e = s_e[t];
-            if (e == -2) continue;
-            if (e < 0 || ge == -1 || (ge >= 0 && e != ge)) { ge = -1; continue; }
-            ge = e;
-            g0 += (g0 & 1ull) ? s_inc1[t] : s_inc0[t];                 // parity in front of chunk t = (entry parity + increments so far) & 1
-            g1 += ((g1 + 1ull) & 1ull) ? s_inc1[t] : s_inc0[t];
+        const unsigned u0 = (unsigned)t0, u1 = (unsigned)t1;           // (< 2^24 wherever e >= 0)
+#pragma unroll
+        for (int k = 0; k < kGeterrGroup; k++) {
+            const int ek = __shfl_sync(0xffffffffu, e, first + k);
+            const unsigned a0 = __shfl_sync(0xffffffffu, u0, first + k), a1 = __shfl_sync(0xffffffffu, u1, first + k);
+            if (ek == -2) continue;
+            if (ek < 0 || ge == -1 || (ge >= 0 && ek != ge)) { ge = -1; continue; }
+            ge = ek;
+            g0 += (g0 & 1ull) ? a1 : a0;                               // parity in front of the chunk = (entry parity + increments so far) & 1
+            g1 += ((g1 + 1ull) & 1ull) ? a1 : a0;
         }
-        s_grp[tid / kGeterrGroup] = ge == -2 ? make_float4(0.0f, 0.0f, 0.0f, 1e38f) : geterr_pack(g0, g1, ge);   // (all empty: + 0, always fine)
+        if (lane == first) s_grp[tid / kGeterrGroup] = ge == -2 ? make_float4(0.0f, 0.0f, 0.0f, 1e38f) : geterr_pack(g0, g1, ge);
     }
     __syncthreads();
     if (tid != 0) return;
@@ -381,7 +384,7 @@ __device__ void geterr_block(const int* __restrict__ ten_base, int nt, float* st
             float4 S = s_sum[g * kGeterrGroup];
             for (int t = g * kGeterrGroup; t < t1; t++) {
                 const float4 Snext = s_sum[min(t + 1, t1 - 1)];
-                if (s_e[t] != -2 && !geterr_try(newerr, S)) {
+                if (!geterr_try(newerr, S)) {
                     const int j0 = min(t * C, nt), j1 = min(j0 + C, nt);
                     for (int i = j0; i < j1; i++) newerr = __fadd_rn(newerr, (float)__ldg(ten_base + i));
                 }
@@ -397,9 +400,10 @@ __device__ void geterr_block(const int* __restrict__ ten_base, int nt, float* st
 // (`by_block`: 1 the block routine, 0 the warp chain, -1 whichever a run would take for this n)
 __global__ void __launch_bounds__(kGeterrThreads) k_geterr(const int* __restrict__ energies, int n, float* state, double rel_tol, int by_block)
 {
+    __shared__ __align__(16) unsigned char s_geterr[kGeterrSmemBytes];
     if (by_block < 0) by_block = n >= kGeterrBlockMin;
-    if (by_block) geterr_block(energies, n, state, rel_tol, threadIdx.x, kGeterrThreads);
-    else if (threadIdx.x < 32) geterr_warp(energies, n, state, rel_tol, threadIdx.x);
+    if (by_block) geterr_block(energies, n, state, rel_tol, threadIdx.x, kGeterrThreads, s_geterr);
+    else if (threadIdx.x < 32) geterr_warp(energies, n, state, rel_tol, threadIdx.x, s_geterr);
 }
 
 // ---- the service block (shared by k_edges and k_setup) ---------------------------------------------
@@ -426,9 +430,11 @@ __device__ void service_block(EvalJob& J, int set, unsigned flags, double rel_to
     __syncthreads();
     // geterr.  Small meshes: the last warp runs the plain chain while the others watch.  Larger ones: the parallel part
     // by everybody, then thread 0 walks the summaries while the others start on the watch.
+    // (their scratch is one buffer: every block of the launch pays for the service block's static shared memory)
+    __shared__ __align__(16) unsigned char s_geterr[kGeterrSmemBytes];
     const bool by_block = J.NT >= kGeterrBlockMin;
-    if (by_block) geterr_block(J.ten[set ^ 1], J.NT, J.err_state, rel_tol, tid, nthreads);
-    else if (tid >= nthreads - 32) geterr_warp(J.ten[set ^ 1], J.NT, J.err_state, rel_tol, tid & 31);
+    if (by_block) geterr_block(J.ten[set ^ 1], J.NT, J.err_state, rel_tol, tid, nthreads, s_geterr);
+    else if (tid >= nthreads - 32) geterr_warp(J.ten[set ^ 1], J.NT, J.err_state, rel_tol, tid & 31, s_geterr);
     if (hist && tid == (by_block ? 0 : nthreads - 32)) J.hist_err[frame - 1] = J.err_state[0];
     if (J.wtri && (by_block || tid < nthreads - 32)) {
         const int watchers = by_block ? nthreads : nthreads - 32;
