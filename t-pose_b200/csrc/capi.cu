@@ -90,6 +90,7 @@ struct tpose_cuda_ctx {
     unsigned* ticket = nullptr;       // [1] topology trigger accumulator ([0] spare)
     float* err_state = nullptr;       // [0] toterr [1] |relerr| [2] newerr [3] converged flag
     int* run_state = nullptr;         // RS_STOP, RS_STEPS, RS_TRIG
+    int4* geterr_scratch = nullptr;   // kGeterrScratchBytes (eval.cuh, geterr_block)
     EvalJob* job_dev = nullptr;       // this context's job record (single launches)
     EvalJob job_host{};               // what job_dev holds
     bool job_valid = false;
@@ -199,6 +200,7 @@ extern "C" int tpose_cuda_create(int device, int max_triangles, int max_points, 
     ctx->err_state = (float*)(ctx->report + 16);
     ctx->wmask = (unsigned*)(ctx->report + 32);
     ctx->pts = (float2*)(ctx->report + ctx->report_pts_off);
+    ALLOC(ctx->geterr_scratch, kGeterrScratchBytes);
     ALLOC(ctx->wbuf, (sizeof(int4) + 3 * sizeof(int)) * (size_t)max_triangles);
     ctx->wtri = (int4*)ctx->wbuf; ctx->whe = (int*)(ctx->wbuf + sizeof(int4) * (size_t)max_triangles);
     ALLOC(ctx->tri, sizeof(int4) * max_triangles);
@@ -271,7 +273,7 @@ extern "C" int tpose_cuda_destroy(tpose_cuda_ctx* ctx)
     for (int s = 0; s < 2; s++) { cudaFree(ctx->cn[s]); cudaFree(ctx->ca[s]); cudaFree(ctx->ten[s]); }
     cudaFree(ctx->staging); cudaFree(ctx->tri);
     cudaFree(ctx->edges); cudaFree(ctx->tri_edges); cudaFree(ctx->corner_off); cudaFree(ctx->corners); cudaFree(ctx->rec);
-    cudaFree(ctx->gr); cudaFree(ctx->wbuf); cudaFree(ctx->ticket);
+    cudaFree(ctx->gr); cudaFree(ctx->wbuf); cudaFree(ctx->ticket); cudaFree(ctx->geterr_scratch);
     cudaFree(ctx->report); cudaFree(ctx->ids); cudaFree(ctx->flush); cudaFree(ctx->list_buf);
     cudaFree(ctx->job_dev); cudaFree(ctx->batch_jobs);
     if (ctx->h_report) cudaFreeHost(ctx->h_report);
@@ -697,7 +699,7 @@ static EvalJob make_job(const tpose_cuda_ctx* ctx, int slot, int flavour)
     j.wmask = ctx->wmask;
     j.hist_pts = ctx->d_hist_pts; j.hist_ten = ctx->d_hist_ten; j.hist_err = ctx->d_hist_err; j.hist_mask = ctx->d_hist_mask;
     j.hist_gr = ctx->d_hist_gr;
-    j.err_state = ctx->err_state; j.run_state = ctx->run_state;
+    j.err_state = ctx->err_state; j.run_state = ctx->run_state; j.geterr_scratch = ctx->geterr_scratch;
     j.trig = ctx->ticket + 1;
     return j;
 }
@@ -1781,16 +1783,16 @@ extern "C" int tpose_cuda_geterr(int device, const int32_t* energies, int n, flo
 {
     if (!energies || n < 0 || !toterr_inout) return mview_fail(TPOSE_ERR_ARG, "geterr: bad arguments");
     MviewWs* ws = nullptr;
-    int rc = mview_workspace(device, padded(sizeof(int) * (size_t)(n > 0 ? n : 1)) + padded(4 * sizeof(float)) + 1024, &ws);
+    int rc = mview_workspace(device, padded(sizeof(int) * (size_t)(n > 0 ? n : 1)) + padded(4 * sizeof(float)) + padded(kGeterrScratchBytes) + 1024, &ws);
     if (rc) return rc;
-    int* dE = carve<int>(ws, n > 0 ? n : 1); float* dS = carve<float>(ws, 4);
+    int* dE = carve<int>(ws, n > 0 ? n : 1); float* dS = carve<float>(ws, 4); int4* dScratch = carve<int4>(ws, kGeterrThreads);
     cudaStream_t st = ws->stream;
     const float st4[4] = {*toterr_inout, 0.0f, 0.0f, 0.0f};
     float out4[4];
     if (n > 0) MCK(cudaMemcpyAsync(dE, energies, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
     MCK(cudaMemcpyAsync(dS, st4, sizeof st4, cudaMemcpyHostToDevice, st));
     MCK(cudaEventRecord(ws->e0, st));
-    k_geterr<<<1, kGeterrThreads, 0, st>>>(dE, n, dS, rel_tol, route < 0 ? -1 : (route ? 1 : 0));
+    k_geterr<<<1, kGeterrThreads, 0, st>>>(dE, n, dS, rel_tol, route < 0 ? -1 : (route ? 1 : 0), dScratch);
     MCK(cudaGetLastError());
     MCK(cudaEventRecord(ws->e1, st));
     MCK(cudaMemcpyAsync(out4, dS, sizeof out4, cudaMemcpyDeviceToHost, st));

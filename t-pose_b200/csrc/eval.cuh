@@ -100,6 +100,7 @@ struct EvalJob {
     int2* hist_gr;             // pgradbuf as frame f left it (stays on the device; see tpose_cuda_history_restore_gradient)
     float* err_state;          // [0] toterr [1] |relerr| [2] newerr [3] converged flag of the last check
     int* run_state;            // RS_*
+    int4* geterr_scratch;      // kGeterrScratchBytes (geterr_block)
     unsigned* trig;            // [0] topology trigger accumulator
 };
 
@@ -216,9 +217,9 @@ __device__ int watch_triangle(const EvalJob& J, int t)
 // Nothing is assumed about how well the guess fits: a wrong guess costs time, never a bit.  About one group in two
 // and seven chunks fall back on a 1.5e9 total (seven binades above 2^24).  Model and randomized check against the
 // serial float32 loop: tests/test_geterr_cpu.py; on the device: tests/test_step_gpu.py.
-constexpr int kGeterrThreads = 256, kGeterrGroup = 8;         // (a group sits inside one warp: it is folded with shuffles)
-// scratch of either routine: 256 chunk summaries + 32 group summaries + 8 warp sums | two rounds of 256 floats
-constexpr int kGeterrSmemBytes = kGeterrThreads * 16 + (kGeterrThreads / kGeterrGroup) * 16 + (kGeterrThreads / 32) * 8;
+constexpr int kGeterrThreads = 256, kGeterrGroup = 8;         // 32 groups: one per lane of the warp that walks
+// scratch of geterr_block in GLOBAL memory: one int4 (inc_0, inc_1, guess, -) per thread
+constexpr int kGeterrScratchBytes = kGeterrThreads * 16;
 constexpr int kGeterrBlockMin = 1792;      // below this many energies the plain chain of one warp is quicker (measured:
                                            // chain 8.1 us + 4.4 ns per element, block routine ~12 us + 0.75 ns, kernel alone)
 
@@ -235,13 +236,14 @@ __device__ __forceinline__ void geterr_finish(float newerr, float* state, double
 }
 
 // The literal chain by one warp: every lane loads its share of the next 256 energies (coalesced, converted to float,
-// issued one round ahead of their use) and parks them in shared memory; all lanes then add the same 256 values in
-// index order, four per broadcast 16-byte load.  Elements past nt are +0.0f: s + 0 = s exactly (s is never -0).
-__device__ void geterr_warp(const int* __restrict__ ten_base, int nt, float* state, double rel_tol, int lane, unsigned char* scratch)
+// issued one round ahead of their use), and all lanes add the same 256 values in index order, fetching each from the
+// lane that holds it with a shuffle.  Elements past nt are +0.0f: s + 0 = s exactly (s is never -0).
+// No shared memory on purpose (geterr_block neither): a few KB of it in k_edges make every SM re-split its L1 / shared
+// memory between k_edges and k_corners -- measured, +1.7 us on the cold k_edges and 1.5 % on the warm step.
+__device__ void geterr_warp(const int* __restrict__ ten_base, int nt, float* state, double rel_tol, int lane)
 {
     constexpr int K = 8;                       // registers per lane and round: 32 * K energies per round
-    float (*s_round)[32 * K] = reinterpret_cast<float (*)[32 * K]>(scratch);     // [2]: the round being added | the next one
-    float nxt[K];
+    float cur[K], nxt[K];
     auto load = [&](int base, float (&r)[K]) {
 #pragma unroll
         for (int j = 0; j < K; j++) {
@@ -249,27 +251,16 @@ __device__ void geterr_warp(const int* __restrict__ ten_base, int nt, float* sta
             r[j] = i < nt ? (float)__ldcg(ten_base + i) : 0.0f;
         }
     };
-    auto stage = [&](int buf, const float (&r)[K]) {
-#pragma unroll
-        for (int j = 0; j < K; j++) s_round[buf][32 * j + lane] = r[j];
-    };
     float newerr = 0.0f;
-    load(0, nxt);
-    stage(0, nxt);
-    __syncwarp();
-    int buf = 0;
-    for (int base = 0; base < nt; base += 32 * K, buf ^= 1) {
-        const bool more = base + 32 * K < nt;
-        if (more) load(base + 32 * K, nxt);                  // in flight while this round is added
-        const float4* q = reinterpret_cast<const float4*>(s_round[buf]);
-#pragma unroll 16
-        for (int i = 0; i < 8 * K; i++) {
-            const float4 v = q[i];
-            newerr = __fadd_rn(newerr, v.x); newerr = __fadd_rn(newerr, v.y);
-            newerr = __fadd_rn(newerr, v.z); newerr = __fadd_rn(newerr, v.w);
-        }
-        if (more) stage(buf ^ 1, nxt);
-        __syncwarp();
+    load(0, cur);
+    for (int base = 0; base < nt; base += 32 * K) {
+        if (base + 32 * K < nt) load(base + 32 * K, nxt);
+#pragma unroll
+        for (int j = 0; j < K; j++)
+#pragma unroll
+            for (int l = 0; l < 32; l++) newerr = __fadd_rn(newerr, __shfl_sync(0xffffffffu, cur[j], l));
+#pragma unroll
+        for (int j = 0; j < K; j++) cur[j] = nxt[j];
     }
     if (lane == 0) geterr_finish(newerr, state, rel_tol);
 }
@@ -294,12 +285,16 @@ __device__ __forceinline__ bool geterr_try(float& s, const float4 S)
     return true;
 }
 
-__device__ void geterr_block(const int* __restrict__ ten_base, int nt, float* state, double rel_tol, int tid, int nthreads, unsigned char* scratch)
+__device__ __forceinline__ float4 shfl4(const float4 v, int src)
 {
-    float4* const s_sum = reinterpret_cast<float4*>(scratch);                              // [kGeterrThreads]
-    float4* const s_grp = s_sum + kGeterrThreads;                                           // [kGeterrThreads / kGeterrGroup]
-    unsigned long long* const s_wsum = reinterpret_cast<unsigned long long*>(s_grp + kGeterrThreads / kGeterrGroup);   // [kGeterrThreads / 32]
-    const int T = nthreads;                                    // <= kGeterrThreads (both callers launch 256)
+    return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src), __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
+}
+
+// `scratch`: kGeterrScratchBytes of global memory of this job; nthreads = kGeterrThreads
+__device__ void geterr_block(const int* __restrict__ ten_base, int nt, float* state, double rel_tol, int tid, int nthreads, int4* scratch)
+{
+    __shared__ unsigned long long s_wsum[kGeterrThreads / 32];
+    const int T = nthreads;
     const int C = 4 * ((nt + 4 * T - 1) / (4 * T));            // chunk length, a multiple of 4: 16-byte loads
     const int lane = tid & 31, wid = tid >> 5;
     const int i0 = min(tid * C, nt), i1 = min(i0 + C, nt);
@@ -330,9 +325,9 @@ __device__ void geterr_block(const int* __restrict__ ten_base, int nt, float* st
     unsigned long long P0 = incl - sum;
     for (int w = 0; w < wid; w++) P0 += s_wsum[w];
     // 2. the chunk as a function of the parity of s / U, under the binade of P0 (e: the guess; -1: no summary; -2: empty chunk)
-    int e = -2;
-    unsigned long long t0 = 0ull, t1 = 0ull;                  // increments in units of U for entry parity 0 / 1
     {
+        int e = -2;
+        unsigned long long t0 = 0ull, t1 = 0ull;              // increments in units of U for entry parity 0 / 1
         if (i0 < i1) {
             e = P0 ? 63 - __clzll((long long)P0) : 0;
             const int sh = max(e - 23, 0);
@@ -351,59 +346,48 @@ __device__ void geterr_block(const int* __restrict__ ten_base, int nt, float* st
             }
             if (neg || t0 >= (1ull << 24) || t1 >= (1ull << 24)) e = -1;
         }
-        s_sum[tid] = e == -2 ? make_float4(0.0f, 0.0f, 0.0f, 1e38f) : geterr_pack(t0, t1, e);    // (empty: + 0, always fine)
+        scratch[tid] = make_int4((int)(unsigned)t0, (int)(unsigned)t1, e, 0);
     }
-    // groups of kGeterrGroup chunks with one common guess: every lane folds its group's eight summaries in order
+    __syncthreads();                                           // (orders the block's global writes before the reads below)
+    if (wid != 0) return;
+    // 3. warp 0 walks: lane g holds group g -- its eight chunk summaries and their fold -- and every lane carries the same sum
+    float4 S[kGeterrGroup], G;
     {
-        const int first = lane & ~(kGeterrGroup - 1);
         int ge = -2; unsigned long long g0 = 0ull, g1 = 0ull;
-        const unsigned u0 = (unsigned)t0, u1 = (unsigned)t1;           // (< 2^24 wherever e >= 0)
 #pragma unroll
         for (int k = 0; k < kGeterrGroup; k++) {
-            const int ek = __shfl_sync(0xffffffffu, e, first + k);
-            const unsigned a0 = __shfl_sync(0xffffffffu, u0, first + k), a1 = __shfl_sync(0xffffffffu, u1, first + k);
+            const int4 c = scratch[lane * kGeterrGroup + k];
+            const unsigned a0 = (unsigned)c.x, a1 = (unsigned)c.y; const int ek = c.z;
+            S[k] = ek == -2 ? make_float4(0.0f, 0.0f, 0.0f, 1e38f) : geterr_pack(a0, a1, ek);        // (empty: + 0, always fine)
             if (ek == -2) continue;
             if (ek < 0 || ge == -1 || (ge >= 0 && ek != ge)) { ge = -1; continue; }
             ge = ek;
-            g0 += (g0 & 1ull) ? a1 : a0;                               // parity in front of the chunk = (entry parity + increments so far) & 1
+            g0 += (g0 & 1ull) ? a1 : a0;                       // parity in front of the chunk = (entry parity + increments so far) & 1
             g1 += ((g1 + 1ull) & 1ull) ? a1 : a0;
         }
-        if (lane == first) s_grp[tid / kGeterrGroup] = ge == -2 ? make_float4(0.0f, 0.0f, 0.0f, 1e38f) : geterr_pack(g0, g1, ge);
+        G = ge == -2 ? make_float4(0.0f, 0.0f, 0.0f, 1e38f) : geterr_pack(g0, g1, ge);
     }
-    __syncthreads();
-    if (tid != 0) return;
-    // 3. the real sum walks the summaries
-    // (the next summary is fetched before the current one is tried: the walk is one dependent chain through newerr)
     float newerr = 0.0f;
-    const int ng = (T + kGeterrGroup - 1) / kGeterrGroup;
-    float4 G = s_grp[0];
-    for (int g = 0; g < ng; g++) {
-        const float4 Gnext = s_grp[min(g + 1, ng - 1)];
-        if (!geterr_try(newerr, G)) {
-            const int t1 = min((g + 1) * kGeterrGroup, T);
-            float4 S = s_sum[g * kGeterrGroup];
-            for (int t = g * kGeterrGroup; t < t1; t++) {
-                const float4 Snext = s_sum[min(t + 1, t1 - 1)];
-                if (!geterr_try(newerr, S)) {
-                    const int j0 = min(t * C, nt), j1 = min(j0 + C, nt);
-                    for (int i = j0; i < j1; i++) newerr = __fadd_rn(newerr, (float)__ldg(ten_base + i));
-                }
-                S = Snext;
-            }
+    for (int g = 0; g < 32; g++) {
+        if (geterr_try(newerr, shfl4(G, g))) continue;
+#pragma unroll
+        for (int k = 0; k < kGeterrGroup; k++) {
+            if (geterr_try(newerr, shfl4(S[k], g))) continue;
+            const int t = g * kGeterrGroup + k;
+            const int j0 = min(t * C, nt), j1 = min(j0 + C, nt);
+            for (int i = j0; i < j1; i++) newerr = __fadd_rn(newerr, (float)__ldg(ten_base + i));
         }
-        G = Gnext;
     }
-    geterr_finish(newerr, state, rel_tol);
+    if (lane == 0) geterr_finish(newerr, state, rel_tol);
 }
 
 // geterr over an array of energies on its own (tpose_cuda_geterr): state = err_state
 // (`by_block`: 1 the block routine, 0 the warp chain, -1 whichever a run would take for this n)
-__global__ void __launch_bounds__(kGeterrThreads) k_geterr(const int* __restrict__ energies, int n, float* state, double rel_tol, int by_block)
+__global__ void __launch_bounds__(kGeterrThreads) k_geterr(const int* __restrict__ energies, int n, float* state, double rel_tol, int by_block, int4* scratch)
 {
-    __shared__ __align__(16) unsigned char s_geterr[kGeterrSmemBytes];
     if (by_block < 0) by_block = n >= kGeterrBlockMin;
-    if (by_block) geterr_block(energies, n, state, rel_tol, threadIdx.x, kGeterrThreads, s_geterr);
-    else if (threadIdx.x < 32) geterr_warp(energies, n, state, rel_tol, threadIdx.x, s_geterr);
+    if (by_block) geterr_block(energies, n, state, rel_tol, threadIdx.x, kGeterrThreads, scratch);
+    else if (threadIdx.x < 32) geterr_warp(energies, n, state, rel_tol, threadIdx.x);
 }
 
 // ---- the service block (shared by k_edges and k_setup) ---------------------------------------------
@@ -430,11 +414,9 @@ __device__ void service_block(EvalJob& J, int set, unsigned flags, double rel_to
     __syncthreads();
     // geterr.  Small meshes: the last warp runs the plain chain while the others watch.  Larger ones: the parallel part
     // by everybody, then thread 0 walks the summaries while the others start on the watch.
-    // (their scratch is one buffer: every block of the launch pays for the service block's static shared memory)
-    __shared__ __align__(16) unsigned char s_geterr[kGeterrSmemBytes];
     const bool by_block = J.NT >= kGeterrBlockMin;
-    if (by_block) geterr_block(J.ten[set ^ 1], J.NT, J.err_state, rel_tol, tid, nthreads, s_geterr);
-    else if (tid >= nthreads - 32) geterr_warp(J.ten[set ^ 1], J.NT, J.err_state, rel_tol, tid & 31, s_geterr);
+    if (by_block) geterr_block(J.ten[set ^ 1], J.NT, J.err_state, rel_tol, tid, nthreads, J.geterr_scratch);
+    else if (tid >= nthreads - 32) geterr_warp(J.ten[set ^ 1], J.NT, J.err_state, rel_tol, tid & 31);
     if (hist && tid == (by_block ? 0 : nthreads - 32)) J.hist_err[frame - 1] = J.err_state[0];
     if (J.wtri && (by_block || tid < nthreads - 32)) {
         const int watchers = by_block ? nthreads : nthreads - 32;
