@@ -220,8 +220,11 @@ __device__ int watch_triangle(const EvalJob& J, int t)
 constexpr int kGeterrThreads = 256, kGeterrGroup = 8;         // 32 groups: one per lane of the warp that walks
 // scratch of geterr_block in GLOBAL memory: one int4 (inc_0, inc_1, guess, -) per thread
 constexpr int kGeterrScratchBytes = kGeterrThreads * 16;
-constexpr int kGeterrBlockMin = 1792;      // below this many energies the plain chain of one warp is quicker (measured:
-                                           // chain 8.1 us + 4.4 ns per element, block routine ~12 us + 0.75 ns, kernel alone)
+// Below this many energies a run takes the plain chain.  Kernel alone the routines cross near 1 500 elements (chain
+// 8.1 us + 4.4 ns per element, block routine ~12 us + 0.7 ns); inside k_edges, where the service block shares its SM
+// with walkers, a frame at 3 000 triangles costs the same either way (21.4 / 21.9 us) and the block routine wins from
+// there on (10 000: 26 against 55 us).
+constexpr int kGeterrBlockMin = 3072;
 
 // the verdict of geterr from the new sum
 __device__ __forceinline__ void geterr_finish(float newerr, float* state, double rel_tol)
