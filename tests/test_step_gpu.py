@@ -546,3 +546,33 @@ def test_geterr_on_the_device_equals_the_serial_float_sum(cuda_pkg):
             got, rel, below = cuda_pkg.geterr(x, toterr=float(tot), rel_tol=1e-4, route=route)
             assert got.view(np.uint32) == want.view(np.uint32), (len(x), route, got, want)
             assert rel.view(np.uint32) == wrel.view(np.uint32) and below == (float(wrel) < 1e-4)
+
+
+def test_run_on_a_large_mesh_takes_the_block_geterr_and_matches_the_serial_sum(cuda_pkg, synth):
+    """Above 3 072 triangles the check a run's frames end with is geterr_block (csrc/eval.cuh) inside k_edges' service block:
+    after every run of one frame, toterr and |relerr| equal the serial float32 sum over the base energies the device holds
+    (source/triangulation.hpp:653-674), bit for bit; and a run of several frames equals those single-frame runs."""
+    from geterr_model import serial_f32
+    w, h = 1280, 720
+    ratio = w / h
+    img = synth.make_image(w, h, seed=8)
+    pts, tri, _ = synth.mesh_for(10000, ratio)
+    NT = tri.shape[0]
+    a = cuda_pkg.Context(device=0, max_triangles=NT, max_points=pts.shape[0])
+    b = cuda_pkg.Context(device=0, max_triangles=NT, max_points=pts.shape[0])
+    for c in (a, b):
+        c.set_image(0, img); c.upload(pts, tri, ratio)
+    toterr = np.float32(1.0)
+    for frame in range(4):
+        n, flags, err = a.run(0, cuda_pkg.TRIANGULATE, 1, 1e-30)
+        assert n == 1
+        want = serial_f32(a.retrieve()["ten"][:NT])
+        rel = np.float32(abs(np.float32((toterr - want) / toterr)))
+        assert np.float32(a.get_toterr()).view(np.uint32) == want.view(np.uint32)
+        assert np.float32(err).view(np.uint32) == rel.view(np.uint32)
+        toterr = want
+    n, flags, err = b.run(0, cuda_pkg.TRIANGULATE, 4, 1e-30)
+    assert n == 4 and np.float32(b.get_toterr()).view(np.uint32) == toterr.view(np.uint32)
+    assert np.float32(err).view(np.uint32) == rel.view(np.uint32)
+    assert np.array_equal(a.retrieve()["ten"], b.retrieve()["ten"])
+    a.close(); b.close()
