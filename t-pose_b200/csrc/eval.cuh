@@ -197,10 +197,10 @@ __device__ int watch_triangle(const EvalJob& J, int t)
 // geterr (source/triangulation.hpp:653-674): float32 running sum of the base energies in index order.  Order
 // matters (float addition is not associative), so taken literally it is one dependent chain of NT additions: 4 ns
 // each on this part however the addends are fed (one thread chasing global loads: 28 us at 3 000 triangles; one warp
-// with the round staged in shared memory: 12 us, 41 us at 10 000) -- and k_edges cannot end before its service
-// block does.  What is serial in it is much less than that:
+// fed by shuffles: 12 us, 41 us at 10 000) -- and k_edges cannot end before its service block does.  What is serial
+// in it is much less than that (geterr_block):
 //
-// The sum by the whole service block, exactly, in a few microseconds whatever NT is.  With non-negative addends the running sum s never decreases.  While s < 2^24 every addition is exact.  Inside a
+// With non-negative addends the running sum s never decreases.  While s < 2^24 every addition is exact.  Inside a
 // binade [2^e, 2^(e+1)), e >= 24, s is a multiple of U = 2^(e-23) and adding a = q U + r (0 <= r < U) gives
 // s + U (q + c): c = 0 if r < U/2, 1 if r > U/2, and on an exact tie (r = U/2, round to even) c = parity of (s/U + q).
 // So as long as the sum stays inside one binade, a run of additions is a function of ONE bit of s -- the parity of
@@ -208,15 +208,15 @@ __device__ int watch_triangle(const EvalJob& J, int t)
 // such runs compose: inc_p = A.inc_p + B.inc_[(p + A.inc_p) & 1].
 //   1. every thread takes a contiguous chunk, sums it exactly (int64) and a block scan gives the exact prefix P in
 //      front of the chunk; the binade of P is the thread's GUESS for the binade the float sum is in there;
-//   2. the thread folds its chunk into (inc_0, inc_1) under that guess; groups of 8 threads with the same guess are
-//      folded once more;
-//   3. one thread walks the 32 groups with the real float sum: a summary is used only if the sum is in the guessed
-//      binade before it and still in it after it (monotone: then it was there all the way, and the increment is
-//      exact) -- otherwise the group's 8 thread summaries are tried the same way, and a chunk whose summary fails
-//      (it straddles a power of two, holds a negative energy, ...) is added the plain way, one FADD per element.
-// Nothing is assumed about how well the guess fits: a wrong guess costs time, never a bit.  About one group in two
+//   2. the thread folds its chunk into (inc_0, inc_1) under that guess and leaves it in the job's global scratch;
+//   3. warp 0 walks with the real float sum (the same in every lane): lane g holds group g -- eight chunk summaries and
+//      their fold -- and hands them round with shuffles.  A summary is used only if the sum is in the guessed binade
+//      before it and still in it after it (monotone: then it was there all the way, and the increment is exact);
+//      otherwise the group's eight chunk summaries are tried the same way, and a chunk whose summary fails (it
+//      straddles a power of two, holds a negative energy, ...) is added the plain way, one FADD per element.
+// Nothing is assumed about how well the guess fits: a wrong guess costs time, never a bit.  About one group in four
 // and seven chunks fall back on a 1.5e9 total (seven binades above 2^24).  Model and randomized check against the
-// serial float32 loop: tests/test_geterr_cpu.py; on the device: tests/test_step_gpu.py.
+// serial float32 loop: tests/geterr_model.py + tests/test_geterr_cpu.py; on the device: tests/test_step_gpu.py.
 constexpr int kGeterrThreads = 256, kGeterrGroup = 8;         // 32 groups: one per lane of the warp that walks
 // scratch of geterr_block in GLOBAL memory: one int4 (inc_0, inc_1, guess, -) per thread
 constexpr int kGeterrScratchBytes = kGeterrThreads * 16;
